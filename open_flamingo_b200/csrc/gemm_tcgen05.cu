@@ -1,0 +1,467 @@
+// bf16 x bf16 -> fp32 GEMM for sm_100a: TMA-staged operands (128B swizzle), tcgen05.mma with the
+// accumulator in TMEM (double buffered), warp-specialised persistent CTAs, fused epilogues.
+//
+//   out[m, n] = epilogue( sum_k A(m, k) * B(n, k) )
+//
+// Operand storage ("major"):
+//   K-major  : X is [rows, K] row-major (K contiguous)             -- forward  Y = X W^T
+//   MN-major : X is [K, rows] row-major (rows contiguous)          -- dgrad (B = W) / wgrad (A = dY, B = X)
+// so no transposed copies of weights or activations are ever materialised.
+//
+// This kernel replaces every nn.Linear on the reference hot path:
+//   helpers.py:15-22 (FeedForward), :35-37 / :52-54 / :65 (PerceiverAttention to_q/to_kv/to_out),
+//   :153-155 / :186-189 / :233 (MaskedCrossAttention to_q/to_kv/to_out), and the gate/residual
+//   arithmetic of helpers.py:267-277 in its epilogue; plus the open_clip ViT linears (third party).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "ofk_internal.h"
+#include "ofk_ptx.cuh"
+
+namespace ofk {
+
+constexpr int BM = 128;       // UMMA_M (cta_group::1)
+constexpr int BK = 64;        // one 128-byte swizzle atom of bf16
+constexpr int UMMA_K = 16;    // fixed for 16-bit inputs
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_WARP0 = 4;  // warps 4..7 are the epilogue (warp % 4 == TMEM lane quarter)
+
+struct GemmParams {
+  int M, N, K;
+  int splits;        // split-K factor (>1 only with the atomic epilogue)
+  int kb_per_split;  // k-blocks per split
+  void* out;
+  long long ldo;
+  void* out2;
+  long long ldo2;
+  const void* aux;
+  long long ldaux;
+  const float* bias;
+  const float* gate;
+};
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int A_BYTES = BM * BK * 2;   // 16 KiB
+  static constexpr int B_BYTES = BN * BK * 2;   // 16/32 KiB
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
+};
+
+// ----------------------------------------------------------------------------------------------
+// Epilogue: 16 consecutive accumulator columns of one output row per call.
+template <int EPI>
+__device__ __forceinline__ void epilogue16(const GemmParams& p, float gate_t, int row, int col,
+                                           const uint32_t (&acc)[16]) {
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[i]);
+
+  if constexpr (EPI == OFK_EPI_STORE_BF16 || EPI == OFK_EPI_BIAS_BF16 || EPI == OFK_EPI_BIAS_QGELU_BF16) {
+    if constexpr (EPI != OFK_EPI_STORE_BF16) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4 b = __ldg(b4 + i);
+        v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+      }
+    }
+    if constexpr (EPI == OFK_EPI_BIAS_QGELU_BF16) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = quick_gelu(bf16_round(v[i]));
+    }
+    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col);
+    o[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    o[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+  } else if constexpr (EPI == OFK_EPI_STORE_F32) {
+    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else if constexpr (EPI == OFK_EPI_ATOMIC_F32) {
+    float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * i), "f"(v[4 * i]),
+                   "f"(v[4 * i + 1]), "f"(v[4 * i + 2]), "f"(v[4 * i + 3])
+                   : "memory");
+    }
+  } else if constexpr (EPI == OFK_EPI_GELU_DUAL) {
+    // z = bf16(acc) is what the reference's Linear emits under autocast; GELU is taken of that.
+    float g[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { v[i] = bf16_round(v[i]); g[i] = gelu_exact(v[i]); }
+    uint4* z = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col);
+    uint4* h = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + (long long)row * p.ldo2 + col);
+    z[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    z[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+    h[0] = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
+    h[1] = make_uint4(pack_bf16x2(g[8], g[9]), pack_bf16x2(g[10], g[11]), pack_bf16x2(g[12], g[13]), pack_bf16x2(g[14], g[15]));
+  } else if constexpr (EPI == OFK_EPI_GATE_RESID_F32 || EPI == OFK_EPI_BIAS_RESID_F32) {
+    // out = branch * tanh(gate) + residual (fp32 residual stream); branch kept in bf16 for the gate grad.
+    if constexpr (EPI == OFK_EPI_BIAS_RESID_F32) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4 b = __ldg(b4 + i);
+        v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = bf16_round(v[i]);
+    if (p.out2 != nullptr) {
+      uint4* br = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + (long long)row * p.ldo2 + col);
+      br[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+      br[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+    }
+    const float4* r4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.aux) + (long long)row * p.ldaux + col);
+    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 r = r4[i];
+      o[i] = make_float4(fmaf(v[4 * i], gate_t, r.x), fmaf(v[4 * i + 1], gate_t, r.y),
+                         fmaf(v[4 * i + 2], gate_t, r.z), fmaf(v[4 * i + 3], gate_t, r.w));
+    }
+  } else if constexpr (EPI == OFK_EPI_DGELU_BF16) {
+    // out = bf16( bf16(acc) * gelu'(z) ), z = saved bf16 pre-activation
+    const uint4* z4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + (long long)row * p.ldaux + col);
+    uint4 za = z4[0], zb = z4[1];
+    uint32_t zw[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[2 * i] = bf16_round(v[2 * i]) * gelu_exact_grad(bf16_lo(zw[i]));
+      v[2 * i + 1] = bf16_round(v[2 * i + 1]) * gelu_exact_grad(bf16_hi(zw[i]));
+    }
+    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col);
+    o[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    o[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+template <int BN, int A_MN, int B_MN, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+            const GemmParams p) {
+  using L = SmemLayout<BN>;
+  constexpr int STAGES = L::STAGES;
+  constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages (256 or 512 columns)
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = (p.M + BM - 1) / BM;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int num_work = m_tiles * n_tiles * p.splits;
+  const int total_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one thread) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int mt = w % m_tiles;
+        const int rest = w / m_tiles;
+        const int nt = rest % n_tiles;
+        const int ks = rest / n_tiles;
+        const int m0 = mt * BM, n0 = nt * BN;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(total_kb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          const int k0 = kb * BK;
+          if constexpr (A_MN == 0) {
+            tma_load_2d(sa, &tma_a, &full_bar[stage], k0, m0);             // box {64 k, 128 rows}
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i)                               // boxes {64 mn, 64 k}
+              tma_load_2d(sa + i * (BK * 128), &tma_a, &full_bar[stage], m0 + 64 * i, k0);
+          }
+          if constexpr (B_MN == 0) {
+            tma_load_2d(sb, &tma_b, &full_bar[stage], k0, n0);             // box {64 k, BN rows}
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              tma_load_2d(sb + i * (BK * 128), &tma_b, &full_bar[stage], n0 + 64 * i, k0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aphase = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int ks = (w / m_tiles) / n_tiles;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(total_kb, kb0 + p.kb_per_split);
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // K-major : 8-row groups 1024 B apart (SBO); advance 32 B per UMMA_K inside the swizzle atom.
+            // MN-major: 64-wide MN chunks BK*128 B apart (LBO), 8-k groups 1024 B apart (SBO);
+            //           advance 2 k-groups = 2048 B per UMMA_K.
+            const uint64_t adesc = A_MN ? make_smem_desc_sw128(sa + k * 2048, BK * 128, 1024)
+                                        : make_smem_desc_sw128(sa + k * 32, 0, 1024);
+            const uint64_t bdesc = B_MN ? make_smem_desc_sw128(sb + k * 2048, BK * 128, 1024)
+                                        : make_smem_desc_sw128(sb + k * 32, 0, 1024);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[as]);       // accumulator ready for the epilogue
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= EPI_WARP0) {
+    // ===================== epilogue (4 warps; TMEM -> regs -> fused op -> global) =====================
+    const int q = warp - EPI_WARP0;  // TMEM lane quarter == warp % 4
+    float gate_t = 1.0f;
+    if constexpr (EPI == OFK_EPI_GATE_RESID_F32) {
+      if (p.gate != nullptr) gate_t = tanhf(__ldg(p.gate));
+    }
+    int as = 0; uint32_t aphase = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      const int mt = w % m_tiles;
+      const int nt = (w / m_tiles) % n_tiles;
+      const int row = mt * BM + q * 32 + lane;
+      const int n0 = nt * BN;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+#pragma unroll 2
+      for (int c = 0; c < BN / 16; ++c) {
+        uint32_t acc[16];
+        tmem_ld16(taddr + c * 16, acc);
+        tmem_ld_wait();
+        const int col = n0 + c * 16;
+        if (row < p.M && col < p.N) epilogue16<EPI>(p, gate_t, row, col, acc);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Host side: tensor-map cache + dispatch.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr; long long ld; int rows, cols, box_inner, box_outer;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && ld == o.ld && rows == o.rows && cols == o.cols && box_inner == o.box_inner &&
+           box_outer == o.box_outer;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    h = h * 1000003u ^ (size_t)k.ld; h = h * 1000003u ^ (size_t)k.rows; h = h * 1000003u ^ (size_t)k.cols;
+    h = h * 1000003u ^ (size_t)(k.box_inner * 1024 + k.box_outer);
+    return h;
+  }
+};
+
+// 2-D bf16 row-major tensor [rows, cols] (cols contiguous, row stride ld elements), 128B swizzle.
+static int get_tensor_map(const void* ptr, long long ld, int rows, int cols, int box_inner, int box_outer,
+                          CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{ptr, ld, rows, cols, box_inner, box_outer};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return 0; }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return ofk_set_error(OFK_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not found");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 2) & 15))
+    return ofk_set_error(OFK_ERR_ALIGN, "GEMM operand must be 16-byte aligned with a 16-byte-multiple row stride");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%lld box=%dx%d", (int)r, rows,
+             cols, ld, box_inner, box_outer);
+    return ofk_set_error(OFK_ERR_DRIVER, buf);
+  }
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache.emplace(key, m);
+  }
+  *out = m;
+  return 0;
+}
+
+static int g_num_sms = 0;
+
+template <int BN, int A_MN, int B_MN, int EPI>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  using L = SmemLayout<BN>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) return ofk_set_error(OFK_ERR_CUDA, cudaGetErrorString(e));
+    attr_done = true;
+  }
+  const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
+  const int work = m_tiles * n_tiles * p.splits;
+  const int grid = work < g_num_sms ? work : g_num_sms;
+  kern<<<grid, NUM_THREADS, L::TOTAL, stream>>>(ta, tb, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return ofk_set_error(OFK_ERR_CUDA, cudaGetErrorString(e));
+  ofk_count_launch();
+  return 0;
+}
+
+template <int BN, int EPI>
+static int dispatch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                          cudaStream_t s) {
+  if (a_mn == 0 && b_mn == 0) return launch<BN, 0, 0, EPI>(ta, tb, p, s);
+  if (a_mn == 0 && b_mn == 1) return launch<BN, 0, 1, EPI>(ta, tb, p, s);
+  if (a_mn == 1 && b_mn == 1) return launch<BN, 1, 1, EPI>(ta, tb, p, s);
+  return launch<BN, 1, 0, EPI>(ta, tb, p, s);
+}
+
+template <int BN>
+static int dispatch_epi(int epi, int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb,
+                        const GemmParams& p, cudaStream_t s) {
+  switch (epi) {
+    case OFK_EPI_STORE_BF16: return dispatch_major<BN, OFK_EPI_STORE_BF16>(a_mn, b_mn, ta, tb, p, s);
+    case OFK_EPI_STORE_F32: return dispatch_major<BN, OFK_EPI_STORE_F32>(a_mn, b_mn, ta, tb, p, s);
+    case OFK_EPI_ATOMIC_F32: return dispatch_major<BN, OFK_EPI_ATOMIC_F32>(a_mn, b_mn, ta, tb, p, s);
+    case OFK_EPI_BIAS_BF16: return dispatch_major<BN, OFK_EPI_BIAS_BF16>(a_mn, b_mn, ta, tb, p, s);
+    case OFK_EPI_BIAS_QGELU_BF16: return dispatch_major<BN, OFK_EPI_BIAS_QGELU_BF16>(a_mn, b_mn, ta, tb, p, s);
+    case OFK_EPI_GELU_DUAL: return dispatch_major<BN, OFK_EPI_GELU_DUAL>(a_mn, b_mn, ta, tb, p, s);
+    case OFK_EPI_GATE_RESID_F32: return dispatch_major<BN, OFK_EPI_GATE_RESID_F32>(a_mn, b_mn, ta, tb, p, s);
+    case OFK_EPI_DGELU_BF16: return dispatch_major<BN, OFK_EPI_DGELU_BF16>(a_mn, b_mn, ta, tb, p, s);
+    case OFK_EPI_BIAS_RESID_F32: return dispatch_major<BN, OFK_EPI_BIAS_RESID_F32>(a_mn, b_mn, ta, tb, p, s);
+  }
+  return ofk_set_error(OFK_ERR_ARG, "unknown GEMM epilogue");
+}
+
+}  // namespace ofk
+
+extern "C" int ofk_gemm_bf16(int epi, int a_mn_major, int b_mn_major, const void* A, long long lda, const void* B,
+                             long long ldb, int M, int N, int K, int splits, int block_n, void* out, long long ldo,
+                             void* out2, long long ldo2, const void* aux, long long ldaux, const float* bias,
+                             const float* gate, void* stream_) {
+  using namespace ofk;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (M <= 0 || N <= 0 || K <= 0) return ofk_set_error(OFK_ERR_ARG, "GEMM dims must be positive");
+  if (N % 16 != 0) return ofk_set_error(OFK_ERR_ARG, "GEMM N must be a multiple of 16");
+  if (!A || !B || !out) return ofk_set_error(OFK_ERR_ARG, "GEMM null operand");
+  if (splits < 1) splits = 1;
+  if (splits > 1 && epi != OFK_EPI_ATOMIC_F32) return ofk_set_error(OFK_ERR_ARG, "split-K needs the atomic epilogue");
+  if ((epi == OFK_EPI_BIAS_BF16 || epi == OFK_EPI_BIAS_QGELU_BF16 || epi == OFK_EPI_BIAS_RESID_F32) && !bias)
+    return ofk_set_error(OFK_ERR_ARG, "bias epilogue without bias");
+  if ((epi == OFK_EPI_GATE_RESID_F32 || epi == OFK_EPI_BIAS_RESID_F32 || epi == OFK_EPI_DGELU_BF16) && !aux)
+    return ofk_set_error(OFK_ERR_ARG, "epilogue needs aux operand");
+  if (epi == OFK_EPI_GELU_DUAL && !out2) return ofk_set_error(OFK_ERR_ARG, "GELU_DUAL needs out2");
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) return ofk_set_error(OFK_ERR_CUDA, "no CUDA device");
+  }
+  const int BN = (block_n == 128 || block_n == 256) ? block_n : ((N % 256 == 0 || N > 1024) ? 256 : 128);
+  const int total_kb = (K + BK - 1) / BK;
+  if (splits > total_kb) splits = total_kb;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.kb_per_split = (total_kb + splits - 1) / splits;
+  p.splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
+  p.out = out; p.ldo = ldo; p.out2 = out2; p.ldo2 = ldo2; p.aux = aux; p.ldaux = ldaux; p.bias = bias; p.gate = gate;
+
+  CUtensorMap ta, tb;
+  int rc;
+  // K-major: tensor [rows, K], box {64 (k), tile rows}. MN-major: tensor [K, rows], box {64 (rows), 64 (k)}.
+  rc = a_mn_major ? get_tensor_map(A, lda, K, M, 64, BK, &ta) : get_tensor_map(A, lda, M, K, BK, BM, &ta);
+  if (rc) return rc;
+  rc = b_mn_major ? get_tensor_map(B, ldb, K, N, 64, BK, &tb) : get_tensor_map(B, ldb, N, K, BK, BN, &tb);
+  if (rc) return rc;
+  if (BN == 256) return dispatch_epi<256>(epi, a_mn_major, b_mn_major, ta, tb, p, stream);
+  return dispatch_epi<128>(epi, a_mn_major, b_mn_major, ta, tb, p, stream);
+}
