@@ -70,12 +70,13 @@ int ofk_gemm_bf16(int epi, int a_mn_major, int b_mn_major, const void* A, long l
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm over the last dim (eps inside sqrt, affine), fp32 statistics.  nn.LayerNorm at
  * helpers.py:17,32-33,47-48,105,132,151,184.
- *   x: [rows, D] f32 (ldx) or bf16 (x_is_bf16).  y: bf16 (y_is_f32 = 0) or f32, written at
+ *   x: [rows, D] f32 (ldx).  y: bf16 (y_is_f32 = 0) or f32, written at
  *   row index  (r / rows_per_group) * group_stride + group_offset + r % rows_per_group  of y (ldy) --
  *   this lets two LayerNorms write the two halves of PerceiverAttention's cat((x, latents), -2)
- *   (helpers.py:53) in place.  mean/rstd: [rows] f32 outputs (may be NULL).
+ *   (helpers.py:53) in place (rows_per_group <= 0: identity mapping).  mean/rstd: [rows] f32 outputs (may be
+ *   NULL).  D % 4 == 0, D <= 4096.
  */
-int ofk_layernorm_fwd(const void* x, int x_is_bf16, long long ldx, const float* gamma, const float* beta,
+int ofk_layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta,
                       float eps, int rows, int D, void* y, int y_is_f32, long long ldy, int rows_per_group,
                       int group_stride, int group_offset, float* mean, float* rstd, void* stream);
 

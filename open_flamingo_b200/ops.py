@@ -53,3 +53,192 @@ def gemm(a, b, *, a_mn=False, b_mn=False, epi=L.EPI_STORE_BF16, out=None, out2=N
         out.data_ptr(), out.stride(0), L.ptr(out2), 0 if out2 is None else out2.stride(0),
         L.ptr(aux), 0 if aux is None else aux.stride(0), L.ptr(bias), L.ptr(gate), L.stream_ptr()))
     return out
+
+
+def layernorm_fwd(x, gamma, beta, eps=1e-5, *, out=None, out_f32=False, rows_per_group=0, group_stride=0,
+                  group_offset=0, want_stats=True):
+    """x: [rows, D] f32.  Returns (y, mean, rstd).  `out` may be a larger buffer written with the group mapping."""
+    L.require_cuda(x)
+    _rowmajor_2d(x, "x")
+    if x.dtype != f32:
+        raise ValueError("layernorm input must be float32 (the residual stream is fp32)")
+    rows, D = x.shape
+    if out is None:
+        out = torch.empty((rows, D), device=x.device, dtype=f32 if out_f32 else bf16)
+    _rowmajor_2d(out, "out")
+    y_is_f32 = out.dtype == f32
+    mean = torch.empty(rows, device=x.device, dtype=f32) if want_stats else None
+    rstd = torch.empty(rows, device=x.device, dtype=f32) if want_stats else None
+    L.check(L.lib().ofk_layernorm_fwd(x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(), eps, rows, D,
+                                      out.data_ptr(), int(y_is_f32), out.stride(0), rows_per_group, group_stride,
+                                      group_offset, L.ptr(mean), L.ptr(rstd), L.stream_ptr()))
+    return out, mean, rstd
+
+
+_ln_ws = {}
+
+
+def _ln_workspace(device, rows, D):
+    need = int(L.lib().ofk_layernorm_bwd_workspace(rows, D))
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    ws = _ln_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, device=device, dtype=torch.uint8)
+        _ln_ws[key] = ws
+    return ws
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, *, dgamma=None, dbeta=None, dx=None, dx_add=None, rows_per_group=0,
+                  group_stride=0, group_offset=0):
+    """dx = LN'(dy) (+ dx_add); dgamma/dbeta are accumulated in place.  dy may be bf16 or f32 (mapped rows)."""
+    L.require_cuda(dy, x)
+    _rowmajor_2d(dy, "dy")
+    _rowmajor_2d(x, "x")
+    rows, D = x.shape
+    if dx is None:
+        dx = torch.empty((rows, D), device=x.device, dtype=f32)
+    ws = _ln_workspace(x.device, rows, D)
+    L.check(L.lib().ofk_layernorm_bwd(dy.data_ptr(), int(dy.dtype == f32), dy.stride(0), rows_per_group, group_stride,
+                                      group_offset, x.data_ptr(), x.stride(0), gamma.data_ptr(), mean.data_ptr(),
+                                      rstd.data_ptr(), rows, D, dx.data_ptr(), dx.stride(0), L.ptr(dx_add),
+                                      0 if dx_add is None else dx_add.stride(0), L.ptr(dgamma), L.ptr(dbeta),
+                                      ws.data_ptr(), L.stream_ptr()))
+    return dx
+
+
+def _bstride_ld(t, name):
+    if t.dim() != 3 or t.stride(2) != 1:
+        raise ValueError(f"{name} must be [batch, rows, heads*64] with unit inner stride")
+    return t.stride(0), t.stride(1)
+
+
+def attn_fwd(q, k, v, heads, scale, *, mask_mode=L.MASK_NONE, text_time=None, keys_per_media=64, out=None,
+             want_lse=True):
+    """q: [B, nq, heads*64] (may be a column-slice view), k/v: [B, nk, heads*64].  Returns (o, lse)."""
+    L.require_cuda(q, k, v)
+    B, nq = q.shape[0], q.shape[1]
+    nk = k.shape[1]
+    if q.dtype != bf16 or k.dtype != bf16 or v.dtype != bf16:
+        raise ValueError("attention operands must be bfloat16")
+    if out is None:
+        out = torch.empty((B, nq, heads * 64), device=q.device, dtype=bf16)
+    lse = torch.empty((B, heads, nq), device=q.device, dtype=f32) if want_lse else None
+    qb, ldq = _bstride_ld(q, "q")
+    kb, ldk = _bstride_ld(k, "k")
+    vb, ldv = _bstride_ld(v, "v")
+    ob, ldo = _bstride_ld(out, "out")
+    if mask_mode != L.MASK_NONE:
+        if text_time is None or text_time.dtype != torch.int32 or tuple(text_time.shape) != (B, nq):
+            raise ValueError("media mask needs int32 text_time of shape [B, nq]")
+        text_time = text_time.contiguous()
+    L.check(L.lib().ofk_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), L.ptr(lse), B, heads, nq, nk,
+                                 qb, ldq, kb, ldk, vb, ldv, ob, ldo, scale, mask_mode, L.ptr(text_time), keys_per_media,
+                                 L.stream_ptr()))
+    return out, lse
+
+
+def attn_bwd(q, k, v, o, d_o, lse, heads, scale, *, mask_mode=L.MASK_NONE, text_time=None, keys_per_media=64,
+             dq=None, dk=None, dv=None):
+    """Returns (dq, dk, dv) bf16.  d_o must share o's strides."""
+    L.require_cuda(q, k, v, o, d_o)
+    B, nq = q.shape[0], q.shape[1]
+    nk = k.shape[1]
+    if d_o.stride() != o.stride():
+        raise ValueError("d_o must have the same strides as o")
+    if dq is None:
+        dq = torch.empty((B, nq, heads * 64), device=q.device, dtype=bf16)
+    if dk is None:
+        dk = torch.empty((B, nk, heads * 64), device=q.device, dtype=bf16)
+    if dv is None:
+        dv = torch.empty((B, nk, heads * 64), device=q.device, dtype=bf16)
+    delta = torch.empty((B, heads, nq), device=q.device, dtype=f32)
+    qb, ldq = _bstride_ld(q, "q")
+    kb, ldk = _bstride_ld(k, "k")
+    vb, ldv = _bstride_ld(v, "v")
+    ob, ldo = _bstride_ld(o, "o")
+    dqb, lddq = _bstride_ld(dq, "dq")
+    dkb, lddk = _bstride_ld(dk, "dk")
+    dvb, lddv = _bstride_ld(dv, "dv")
+    if text_time is not None:
+        text_time = text_time.contiguous()
+    L.check(L.lib().ofk_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), d_o.data_ptr(), lse.data_ptr(),
+                                 delta.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, heads, nq, nk,
+                                 qb, ldq, kb, ldk, vb, ldv, ob, ldo, dqb, lddq, dkb, lddk, dvb, lddv, scale, mask_mode,
+                                 L.ptr(text_time), keys_per_media, L.stream_ptr()))
+    return dq, dk, dv
+
+
+def text_time(input_ids=None, media_token_id=0, media_locations=None, use_cached_media=False, t_txt=None):
+    """int32 [B, T_txt] inclusive count of media tokens (helpers.py:199-208)."""
+    src = media_locations if media_locations is not None else input_ids
+    L.require_cuda(src)
+    B = src.shape[0]
+    n_loc = src.shape[1]
+    if t_txt is None:
+        t_txt = n_loc
+    loc = None
+    if media_locations is not None:
+        loc = media_locations.to(torch.uint8).contiguous()
+    ids = None
+    if input_ids is not None and media_locations is None:
+        ids = input_ids.to(torch.int64).contiguous()
+    out = torch.empty((B, t_txt), device=src.device, dtype=torch.int32)
+    L.check(L.lib().ofk_text_time(L.ptr(ids), int(media_token_id), B, t_txt, n_loc, L.ptr(loc), int(use_cached_media),
+                                  out.data_ptr(), L.stream_ptr()))
+    return out
+
+
+def cast_bf16(src, out=None):
+    L.require_cuda(src)
+    src = src.contiguous()
+    if out is None:
+        out = torch.empty(src.shape, device=src.device, dtype=bf16)
+    L.check(L.lib().ofk_cast_f32_bf16(src.data_ptr(), out.data_ptr(), src.numel(), L.stream_ptr()))
+    return out
+
+
+def gate_bwd(dout, branch, gate, dgate):
+    """dbranch(bf16) = dout * tanh(gate); dgate += (1 - tanh^2) * <dout, branch>.  gate None: plain cast."""
+    L.require_cuda(dout)
+    if not dout.is_contiguous() or (branch is not None and not branch.is_contiguous()):
+        raise ValueError("gate_bwd operands must be contiguous")
+    dbranch = torch.empty(dout.shape, device=dout.device, dtype=bf16)
+    L.check(L.lib().ofk_gate_bwd(dout.data_ptr(), L.ptr(branch), L.ptr(gate), dbranch.data_ptr(), L.ptr(dgate),
+                                 dout.numel(), L.stream_ptr()))
+    return dbranch
+
+
+def add_(dst, src):
+    L.check(L.lib().ofk_add_f32(dst.data_ptr(), src.data_ptr(), dst.numel(), L.stream_ptr()))
+    return dst
+
+
+def patchify(images, patch, ldp):
+    """images [n,3,H,W] f32 -> [n*g, ldp] bf16 patch rows (conv-weight column order), zero padded."""
+    L.require_cuda(images)
+    images = images.contiguous()
+    n, _, H, W = images.shape
+    g = (H // patch) * (W // patch)
+    out = torch.empty((n * g, ldp), device=images.device, dtype=bf16)
+    L.check(L.lib().ofk_patchify(images.data_ptr(), n, H, W, patch, out.data_ptr(), ldp, L.stream_ptr()))
+    return out
+
+
+def vit_assemble(patch_emb, class_emb, pos_emb, n, g, D):
+    tok = torch.empty((n * (g + 1), D), device=patch_emb.device, dtype=f32)
+    L.check(L.lib().ofk_vit_assemble(patch_emb.data_ptr(), class_emb.data_ptr(), pos_emb.data_ptr(), n, g, D,
+                                     tok.data_ptr(), L.stream_ptr()))
+    return tok
+
+
+def adamw_(param, grad, exp_avg, exp_avg_sq, w_bf16, lr, beta1, beta2, eps, wd, step, clip_scale=None):
+    bc1 = 1.0 - beta1 ** step
+    bc2 = 1.0 - beta2 ** step
+    L.check(L.lib().ofk_adamw(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                              L.ptr(w_bf16), param.numel(), lr, beta1, beta2, eps, wd, bc1, bc2, L.ptr(clip_scale),
+                              L.stream_ptr()))
+
+
+def sumsq_(x, out):
+    L.check(L.lib().ofk_sumsq(x.data_ptr(), x.numel(), out.data_ptr(), L.stream_ptr()))
+    return out
