@@ -44,7 +44,8 @@ enum {
   OFK_EPI_GATE_RESID_F32 = 6,  /* out(f32) = bf16(acc)*tanh(*gate) + aux(f32); out2(bf16)=acc (optional; gate NULL => 1)
                                   helpers.py:267-277 (x = branch * gate.tanh() + x), helpers.py:130-131 (Perceiver residuals)   */
   OFK_EPI_DGELU_BF16 = 7,      /* out(bf16) = acc * gelu_erf'(aux(bf16) = z)                 autograd of helpers.py:20           */
-  OFK_EPI_BIAS_RESID_F32 = 8   /* out(f32) = bf16(acc + bias[n]) + aux(f32)                  ViT residual adds                  */
+  OFK_EPI_BIAS_RESID_F32 = 8,  /* out(f32) = bf16(acc + bias[n]) + aux(f32)  (out may alias aux)  ViT residual adds            */
+  OFK_EPI_BIAS_GELU_BF16 = 9   /* out(bf16) = gelu_erf(acc + bias[n])                        ViT mlp.c_fc + nn.GELU (non-openai) */
 };
 
 const char* ofk_last_error(void);
@@ -81,7 +82,8 @@ int ofk_layernorm_fwd(const float* x, long long ldx, const float* gamma, const f
                       int group_stride, int group_offset, float* mean, float* rstd, void* stream);
 
 /* LayerNorm backward.  dy: [rows, D] bf16 or f32 (same row mapping as fwd via dy_* group args);
- * x: f32 [rows, D]; dx(f32) = LN'(dy) (+ dx_add if non-NULL; dx_add may alias dx).
+ * x: f32 [rows, D]; dx(f32) = LN'(dy) (+ dx_add if non-NULL; dx_add may alias dx); dx NULL = parameter
+ * gradients only (PerceiverAttention.norm_media: its input, the frozen ViT features, needs no gradient).
  * dgamma/dbeta (f32 [D]) are ACCUMULATED (+=).  workspace: >= ofk_layernorm_bwd_workspace(rows, D) bytes. */
 long long ofk_layernorm_bwd_workspace(int rows, int D);
 int ofk_layernorm_bwd(const void* dy, int dy_is_f32, long long lddy, int rows_per_group, int group_stride,

@@ -26,6 +26,7 @@ EPI_GELU_DUAL = 5
 EPI_GATE_RESID_F32 = 6
 EPI_DGELU_BF16 = 7
 EPI_BIAS_RESID_F32 = 8
+EPI_BIAS_GELU_BF16 = 9
 
 MASK_NONE = 0
 MASK_MEDIA_EQ = 1

@@ -65,7 +65,8 @@ __device__ __forceinline__ void epilogue16(const GemmParams& p, float gate_t, in
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[i]);
 
-  if constexpr (EPI == OFK_EPI_STORE_BF16 || EPI == OFK_EPI_BIAS_BF16 || EPI == OFK_EPI_BIAS_QGELU_BF16) {
+  if constexpr (EPI == OFK_EPI_STORE_BF16 || EPI == OFK_EPI_BIAS_BF16 || EPI == OFK_EPI_BIAS_QGELU_BF16 ||
+                EPI == OFK_EPI_BIAS_GELU_BF16) {
     if constexpr (EPI != OFK_EPI_STORE_BF16) {
       const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
@@ -77,6 +78,10 @@ __device__ __forceinline__ void epilogue16(const GemmParams& p, float gate_t, in
     if constexpr (EPI == OFK_EPI_BIAS_QGELU_BF16) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = quick_gelu(bf16_round(v[i]));
+    }
+    if constexpr (EPI == OFK_EPI_BIAS_GELU_BF16) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = gelu_exact(bf16_round(v[i]));
     }
     uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col);
     o[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
@@ -418,6 +423,7 @@ static int dispatch_epi(int epi, int a_mn, int b_mn, const CUtensorMap& ta, cons
     case OFK_EPI_GATE_RESID_F32: return dispatch_major<BN, OFK_EPI_GATE_RESID_F32>(a_mn, b_mn, ta, tb, p, s);
     case OFK_EPI_DGELU_BF16: return dispatch_major<BN, OFK_EPI_DGELU_BF16>(a_mn, b_mn, ta, tb, p, s);
     case OFK_EPI_BIAS_RESID_F32: return dispatch_major<BN, OFK_EPI_BIAS_RESID_F32>(a_mn, b_mn, ta, tb, p, s);
+    case OFK_EPI_BIAS_GELU_BF16: return dispatch_major<BN, OFK_EPI_BIAS_GELU_BF16>(a_mn, b_mn, ta, tb, p, s);
   }
   return ofk_set_error(OFK_ERR_ARG, "unknown GEMM epilogue");
 }
@@ -435,7 +441,8 @@ extern "C" int ofk_gemm_bf16(int epi, int a_mn_major, int b_mn_major, const void
   if (!A || !B || !out) return ofk_set_error(OFK_ERR_ARG, "GEMM null operand");
   if (splits < 1) splits = 1;
   if (splits > 1 && epi != OFK_EPI_ATOMIC_F32) return ofk_set_error(OFK_ERR_ARG, "split-K needs the atomic epilogue");
-  if ((epi == OFK_EPI_BIAS_BF16 || epi == OFK_EPI_BIAS_QGELU_BF16 || epi == OFK_EPI_BIAS_RESID_F32) && !bias)
+  if ((epi == OFK_EPI_BIAS_BF16 || epi == OFK_EPI_BIAS_QGELU_BF16 || epi == OFK_EPI_BIAS_RESID_F32 ||
+       epi == OFK_EPI_BIAS_GELU_BF16) && !bias)
     return ofk_set_error(OFK_ERR_ARG, "bias epilogue without bias");
   if ((epi == OFK_EPI_GATE_RESID_F32 || epi == OFK_EPI_BIAS_RESID_F32 || epi == OFK_EPI_DGELU_BF16) && !aux)
     return ofk_set_error(OFK_ERR_ARG, "epilogue needs aux operand");

@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(LNB_THREADS) ln_bwd_kernel(
           const float4 a = *reinterpret_cast<const float4*>(dx_add + (long long)r * ldadd + c);
           o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
         }
-        *reinterpret_cast<float4*>(dx + (long long)r * lddx + c) = o;
+        if (dx) *reinterpret_cast<float4*>(dx + (long long)r * lddx + c) = o;
         dg[g].x += dyv[g].x * xh[g].x; dg[g].y += dyv[g].y * xh[g].y; dg[g].z += dyv[g].z * xh[g].z; dg[g].w += dyv[g].w * xh[g].w;
         db[g].x += dyv[g].x; db[g].y += dyv[g].y; db[g].z += dyv[g].z; db[g].w += dyv[g].w;
       }
@@ -204,7 +204,8 @@ extern "C" int ofk_layernorm_bwd(const void* dy, int dy_is_f32, long long lddy, 
                                  const float* rstd, int rows, int D, float* dx, long long lddx, const float* dx_add,
                                  long long ldadd, float* dgamma, float* dbeta, void* workspace, void* stream_) {
   using namespace ofk;
-  if (!dy || !x || !gamma || !mean || !rstd || !dx || !workspace) return ofk_set_error(OFK_ERR_ARG, "layernorm bwd: null pointer");
+  if (!dy || !x || !gamma || !mean || !rstd || !workspace) return ofk_set_error(OFK_ERR_ARG, "layernorm bwd: null pointer");
+  if (!dx && !dgamma && !dbeta) return 0;
   if (rows <= 0) return 0;
   if (D <= 0 || D % 4 != 0 || D > 4096) return ofk_set_error(OFK_ERR_ARG, "layernorm bwd: D must be a multiple of 4, <= 4096");
   if (ldx % 4 != 0 || lddy % 4 != 0 || lddx % 4 != 0 || (dx_add && ldadd % 4 != 0))

@@ -89,18 +89,19 @@ def _ln_workspace(device, rows, D):
 
 
 def layernorm_bwd(dy, x, gamma, mean, rstd, *, dgamma=None, dbeta=None, dx=None, dx_add=None, rows_per_group=0,
-                  group_stride=0, group_offset=0):
-    """dx = LN'(dy) (+ dx_add); dgamma/dbeta are accumulated in place.  dy may be bf16 or f32 (mapped rows)."""
+                  group_stride=0, group_offset=0, want_dx=True):
+    """dx = LN'(dy) (+ dx_add); dgamma/dbeta are accumulated in place.  dy may be bf16 or f32 (mapped rows).
+    want_dx=False: only the affine-parameter gradients are produced."""
     L.require_cuda(dy, x)
     _rowmajor_2d(dy, "dy")
     _rowmajor_2d(x, "x")
     rows, D = x.shape
-    if dx is None:
+    if dx is None and want_dx:
         dx = torch.empty((rows, D), device=x.device, dtype=f32)
     ws = _ln_workspace(x.device, rows, D)
     L.check(L.lib().ofk_layernorm_bwd(dy.data_ptr(), int(dy.dtype == f32), dy.stride(0), rows_per_group, group_stride,
                                       group_offset, x.data_ptr(), x.stride(0), gamma.data_ptr(), mean.data_ptr(),
-                                      rstd.data_ptr(), rows, D, dx.data_ptr(), dx.stride(0), L.ptr(dx_add),
+                                      rstd.data_ptr(), rows, D, L.ptr(dx), 0 if dx is None else dx.stride(0), L.ptr(dx_add),
                                       0 if dx_add is None else dx_add.stride(0), L.ptr(dgamma), L.ptr(dbeta),
                                       ws.data_ptr(), L.stream_ptr()))
     return dx

@@ -1,0 +1,108 @@
+"""Language-model side of Flamingo: the per-layer wrapper and the mixin spliced onto a HF causal LM.
+
+Interface parity with the reference's open_flamingo/src/flamingo_lm.py:
+  FlamingoLayer  (:6-66)   -- gated cross-attention block (or None) in front of one frozen decoder block
+  FlamingoLMMixin (:69-167) -- init_flamingo / forward / is_conditioned / clear_conditioned_layers, plus the
+                               `gated_cross_attn_layers` and `old_decoder_blocks` attributes whose names
+                               appear in released checkpoints (train_utils.py:321-330).
+The gated blocks are the kernel-backed ones from .helpers; the decoder blocks stay the frozen LM's own
+PyTorch modules.
+"""
+import torch.nn as nn
+
+from .helpers import GatedCrossAttentionBlock
+from .utils import getattr_recursive, setattr_recursive
+
+
+class FlamingoLayer(nn.Module):
+    def __init__(self, gated_cross_attn_layer, decoder_layer, gradient_checkpointing=False):
+        super().__init__()
+        self.gated_cross_attn_layer = gated_cross_attn_layer
+        self.decoder_layer = decoder_layer
+        self.vis_x = None
+        self.media_locations = None
+        self.use_cached_media = None
+        # kept for API compatibility (train.py:368-381); the fused blocks already store only what backward needs
+        if gated_cross_attn_layer is not None:
+            gated_cross_attn_layer._use_gradient_checkpointing = gradient_checkpointing
+        decoder_layer._use_gradient_checkpointing = gradient_checkpointing
+
+    def is_conditioned(self) -> bool:
+        return self.vis_x is not None and self.media_locations is not None
+
+    def condition_vis_x(self, vis_x):
+        self.vis_x = vis_x
+
+    def condition_media_locations(self, media_locations):
+        self.media_locations = media_locations
+
+    def condition_use_cached_media(self, use_cached_media):
+        self.use_cached_media = use_cached_media
+
+    def forward(self, lang_x, attention_mask=None, **decoder_layer_kwargs):
+        xattn = self.gated_cross_attn_layer
+        if xattn is not None:
+            # same failure modes as the reference (flamingo_lm.py:47-53)
+            if self.vis_x is None:
+                raise ValueError("vis_x must be conditioned before forward pass")
+            if self.media_locations is None:
+                raise ValueError("media_locations must be conditioned before forward pass")
+            lang_x = xattn(lang_x, self.vis_x, media_locations=self.media_locations,
+                           use_cached_media=self.use_cached_media)
+        return self.decoder_layer(lang_x, attention_mask=attention_mask, **decoder_layer_kwargs)
+
+
+class FlamingoLMMixin(nn.Module):
+    """Mixed into a HF causal LM instance with utils.extend_instance (factory.py:85)."""
+
+    def set_decoder_layers_attr_name(self, decoder_layers_attr_name):
+        self.decoder_layers_attr_name = decoder_layers_attr_name
+
+    def _get_decoder_layers(self):
+        return getattr_recursive(self, self.decoder_layers_attr_name)
+
+    def _set_decoder_layers(self, value):
+        setattr_recursive(self, self.decoder_layers_attr_name, value)
+
+    def init_flamingo(self, media_token_id, lang_hidden_size, vis_hidden_size, cross_attn_every_n_layers,
+                      gradient_checkpointing):
+        """Insert a gated block before every n-th decoder block: block i gets one iff (i + 1) % n == 0
+        (flamingo_lm.py:100)."""
+        blocks = self._get_decoder_layers()
+        self.old_decoder_blocks = blocks
+        every = cross_attn_every_n_layers
+        self.gated_cross_attn_layers = nn.ModuleList([
+            GatedCrossAttentionBlock(dim=lang_hidden_size, dim_visual=vis_hidden_size) if (i + 1) % every == 0 else None
+            for i in range(len(blocks))
+        ])
+        self.init_flamingo_layers(gradient_checkpointing)
+        self.media_token_id = media_token_id
+        self.initialized_flamingo = True
+        self._use_cached_vision_x = False
+
+    def init_flamingo_layers(self, gradient_checkpointing):
+        """(Re)build the FlamingoLayer list from gated_cross_attn_layers / old_decoder_blocks."""
+        pairs = zip(self.gated_cross_attn_layers, self.old_decoder_blocks)
+        self._set_decoder_layers(nn.ModuleList([FlamingoLayer(x, blk, gradient_checkpointing) for x, blk in pairs]))
+
+    def forward(self, input_ids, attention_mask, **kwargs):
+        if not getattr(self, "initialized_flamingo", False):
+            raise ValueError("Flamingo layers are not initialized. Please call `init_flamingo` first.")
+        media_locations = input_ids == self.media_token_id
+        # HF generate() feeds one token at a time after the prompt; such calls carry no <image> token and must
+        # keep attending to the last cached image (flamingo_lm.py:137-146).
+        use_cached = bool(self._use_cached_vision_x and self.is_conditioned() and not media_locations.any())
+        for layer in self._get_decoder_layers():
+            if not use_cached:
+                layer.condition_media_locations(media_locations)
+            layer.condition_use_cached_media(use_cached)
+        return super().forward(input_ids=input_ids, attention_mask=attention_mask, **kwargs)
+
+    def is_conditioned(self) -> bool:
+        return all(layer.is_conditioned() for layer in self._get_decoder_layers())
+
+    def clear_conditioned_layers(self):
+        for layer in self._get_decoder_layers():
+            layer.condition_vis_x(None)
+            layer.condition_media_locations(None)
+            layer.condition_use_cached_media(None)
