@@ -175,9 +175,11 @@ class GatedCrossAttentionBlock(nn.Module):
         L.require_cuda(x, media)
         if x.dim() != 3 or media.dim() != 4:
             raise ValueError("expected x (B, T_txt, D) and media (B, T_img, n, Dv)")
-        if not use_cached_media and exists(media_locations):
+        if not use_cached_media:  # helpers.py:175-178 (the reference dereferences media_locations here)
+            if not exists(media_locations):
+                raise AttributeError("media_locations is required unless use_cached_media=True")
             assert media_locations.shape[1] == x.shape[1], (
-                f"media_location.shape is {media_locations.shape} but x.shape is {x.shape}")  # helpers.py:175-178
+                f"media_location.shape is {media_locations.shape} but x.shape is {x.shape}")
         B, T_txt, _ = x.shape
         _, T_img, n, Dv = media.shape
         ctx = get_media_context(media, media_locations, use_cached_media, T_txt)
