@@ -28,6 +28,9 @@ f32 = torch.float32
 
 _w16_cache = {}
 
+# set by train.GradBucket: called with a gated block's parameter tuple once its backward kernels are enqueued
+block_backward_hook = None
+
 
 def w16(param):
     """bf16 operand copy of an fp32 master weight, refreshed when the parameter changes."""
@@ -189,6 +192,8 @@ class GatedXattnBlockFn(torch.autograd.Function):
         if needs[1]:
             dmedia = ops.gemm(dkv, w16(wkv), b_mn=True, epi=L.EPI_STORE_F32).view(ctx.media_shape)
         grads = [sinks[n].result() for n in names]
+        if block_backward_hook is not None:
+            block_backward_hook(ctx.params)
         return (dx.view(B, T, D) if needs[0] else None, dmedia, None, None, None, None, None, *grads)
 
 

@@ -1,0 +1,230 @@
+"""Data-parallel training step for the trainable part of Flamingo (resampler + gated cross-attention blocks).
+
+Replaces, for the B200 path, the reference's DDP wrap + clip + AdamW (train/train.py:364-415,
+train/train_utils.py:94-216):
+
+  * GradBucket -- ONE flat fp32 gradient buffer for all trainable hot-path parameters, laid out in backward
+    completion order (last gated block first, resampler last).  The wgrad GEMM epilogues accumulate straight
+    into it (`param._ofk_grad` views, see fused._GradSink), so there is no per-parameter gradient copy and no
+    DDP bucket copy.  It is cut into a few contiguous chunks; chunk k's NCCL all-reduce (NVLink 5 / NVSwitch,
+    NVLS when available) is launched asynchronously the moment the backward of its last layer has been
+    enqueued, so it overlaps the backward of the earlier layers.  Only these gradients are reduced; frozen
+    parameters never enter a collective (factory.py:104-113).
+  * FlatTrainer -- global-norm clip (train_utils.py:208) and AdamW with the reference's two weight-decay groups
+    (decay on `gated_cross_attn` parameters only, train.py:392-408) as one fused kernel per group over the
+    flat buffers; the same kernel refreshes the bf16 operand copies the next step's GEMMs read.
+
+The host-side layout/chunking/all-reduce logic is backend-agnostic (gloo on CPU in tests, NCCL on GPUs).
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import fused
+
+ALIGN = 64  # elements; keeps every parameter view 256-byte (fp32) / 128-byte (bf16) aligned for TMA
+
+
+def hot_path_parameters(model):
+    """[(name, param)] of the trainable hot-path parameters in backward-completion order."""
+    lm = model.lang_encoder
+    groups = []
+    layers = list(lm.gated_cross_attn_layers)
+    for i in reversed(range(len(layers))):
+        blk = layers[i]
+        if blk is None:
+            continue
+        ps = [(f"lang_encoder.gated_cross_attn_layers.{i}.{n}", p) for n, p in blk.named_parameters() if p.requires_grad]
+        if ps:
+            groups.append(("xattn", i, ps))
+    ps = [(f"perceiver.{n}", p) for n, p in model.perceiver.named_parameters() if p.requires_grad]
+    if ps:
+        groups.append(("perceiver", -1, ps))
+    return groups
+
+
+class GradBucket:
+    """Flat gradient (and optionally parameter) storage with chunked asynchronous all-reduce."""
+
+    def __init__(self, groups, num_chunks=6, process_group=None, flatten_params=True):
+        self.pg = process_group
+        self.groups = groups
+        self.entries = []   # (name, param, offset, numel)
+        off = 0
+        group_end = []
+        for kind, idx, ps in groups:
+            for name, p in ps:
+                self.entries.append((name, p, off, p.numel()))
+                off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+            group_end.append(off)
+        self.total = off
+        first = groups[0][2][0][1]
+        self.device = first.device
+        self.grads = torch.zeros(self.total, device=self.device, dtype=torch.float32)
+        self.params = None
+        if flatten_params:
+            self.params = torch.zeros(self.total, device=self.device, dtype=torch.float32)
+        for name, p, o, n in self.entries:
+            if flatten_params:
+                self.params[o:o + n].view_as(p).copy_(p.data)
+                p.data = self.params[o:o + n].view_as(p)
+            gview = self.grads[o:o + n].view_as(p)
+            p._ofk_grad = gview      # fused wgrad epilogues accumulate here
+            p.grad = gview           # anything autograd produces itself (e.g. latents) accumulates in place too
+        # chunk boundaries fall on group (layer) ends; the xattn groups are spread over num_chunks-1 chunks and the
+        # resampler (whose backward finishes last) is its own chunk.
+        xattn_groups = [g for g in range(len(groups)) if groups[g][0] == "xattn"]
+        per = max(1, math.ceil(len(xattn_groups) / max(1, num_chunks - 1))) if xattn_groups else 1
+        self.chunks = []     # (start, end)
+        self.group_to_chunk = {}
+        start = 0
+        for j, g in enumerate(xattn_groups):
+            last_of_chunk = (j + 1) % per == 0 or j == len(xattn_groups) - 1
+            self.group_to_chunk[g] = len(self.chunks)
+            if last_of_chunk:
+                self.chunks.append((start, group_end[g]))
+                start = group_end[g]
+        if start < self.total:
+            for g in range(len(groups)):
+                if groups[g][0] != "xattn":
+                    self.group_to_chunk[g] = len(self.chunks)
+            self.chunks.append((start, self.total))
+        # the gate parameter identifies a gated block from inside its backward
+        self._gate_to_group = {}
+        for g, (kind, idx, ps) in enumerate(groups):
+            if kind == "xattn":
+                for name, p in ps:
+                    if name.endswith("attn_gate"):
+                        self._gate_to_group[id(p)] = g
+        self._chunk_last_group = {}
+        for g, c in self.group_to_chunk.items():
+            self._chunk_last_group[c] = max(self._chunk_last_group.get(c, -1), g)
+        self._pending = []
+        self._launched = set()
+
+    # -------------------------------------------------------------- distributed
+    @property
+    def world(self):
+        if not (dist.is_available() and dist.is_initialized()):
+            return 1
+        return dist.get_world_size(self.pg)
+
+    def zero(self):
+        self.grads.zero_()
+        self._pending = []
+        self._launched = set()
+
+    def _launch(self, c):
+        if c in self._launched:
+            return
+        self._launched.add(c)
+        if self.world > 1:
+            s, e = self.chunks[c]
+            self._pending.append(dist.all_reduce(self.grads[s:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+
+    def on_block_backward_done(self, params):
+        """Called by fused.GatedXattnBlockFn.backward once a block's gradient kernels are enqueued."""
+        g = self._gate_to_group.get(id(params[5]))  # params[5] is attn_gate
+        if g is None:
+            return
+        c = self.group_to_chunk[g]
+        if self._chunk_last_group[c] == g:   # groups complete in increasing g; the chunk's last group closes it
+            self._launch(c)
+
+    def finish(self):
+        """Launch whatever has not been launched (the resampler chunk) and wait for every all-reduce.
+        After this the buffer holds the SUM over ranks (scaling by 1/world is folded into the optimizer)."""
+        for c in range(len(self.chunks)):
+            self._launch(c)
+        for w in self._pending:
+            w.wait()
+        self._pending = []
+
+    def install_hooks(self):
+        fused.block_backward_hook = self.on_block_backward_done
+
+    def remove_hooks(self):
+        if fused.block_backward_hook == self.on_block_backward_done:
+            fused.block_backward_hook = None
+
+
+class FlatTrainer:
+    """zero_grad() -> (user runs forward/backward) -> step().  CUDA only (fused kernels)."""
+
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.1, max_grad_norm=1.0,
+                 num_chunks=6, process_group=None):
+        from . import ops
+        self.ops = ops
+        self.model = model
+        self.lr, self.betas, self.eps, self.wd, self.max_norm = lr, betas, eps, weight_decay, max_grad_norm
+        groups = hot_path_parameters(model)
+        if not groups:
+            raise ValueError("model has no trainable resampler / gated cross-attention parameters")
+        self.bucket = GradBucket(groups, num_chunks=num_chunks, process_group=process_group)
+        b = self.bucket
+        self.exp_avg = torch.zeros_like(b.params)
+        self.exp_avg_sq = torch.zeros_like(b.params)
+        self.w16 = torch.empty(b.total, device=b.device, dtype=torch.bfloat16)
+        ops.cast_bf16(b.params, out=self.w16)
+        for name, p, o, n in b.entries:
+            p._ofk_w16 = self.w16[o:o + n].view(p.shape)
+        # weight-decay segment: the gated blocks come first in the layout (train.py:392-408 decays only them)
+        self.decay_end = 0
+        ei = 0
+        for kind, idx, ps in groups:
+            for _ in ps:
+                name, p, o, n = b.entries[ei]
+                ei += 1
+                if kind == "xattn":
+                    self.decay_end = o + (n + ALIGN - 1) // ALIGN * ALIGN
+        # trainable parameters outside the hot path (LM input embeddings unless frozen): ordinary torch AdamW
+        flat_ids = {id(p) for _, p, _, _ in b.entries}
+        self.extra = [p for p in model.parameters() if p.requires_grad and id(p) not in flat_ids]
+        self.extra_opt = torch.optim.AdamW(self.extra, lr=lr, betas=betas, eps=eps, weight_decay=0.0) if self.extra else None
+        self.step_count = 0
+        self._sumsq = torch.zeros(1, device=b.device, dtype=torch.float32)
+        b.install_hooks()
+
+    def zero_grad(self):
+        self.bucket.zero()
+        for p in self.extra:
+            p.grad = None
+
+    def step(self):
+        b, ops = self.bucket, self.ops
+        b.finish()
+        world = b.world
+        if self.extra and world > 1:
+            for p in self.extra:
+                if p.grad is not None:
+                    dist.all_reduce(p.grad, group=b.pg)
+        # global grad norm of the MEAN gradient (train_utils.py:208), computed on device, no host sync
+        self._sumsq.zero_()
+        ops.sumsq_(b.grads, self._sumsq)
+        sumsq = self._sumsq
+        for p in self.extra:
+            if p.grad is not None:
+                sumsq = sumsq + p.grad.float().pow(2).sum()
+        inv_world = 1.0 / world
+        norm = sumsq.sqrt() * inv_world
+        clip = torch.clamp(self.max_norm / (norm + 1e-6), max=1.0) * inv_world if self.max_norm else \
+            torch.full_like(norm, inv_world)
+        clip = clip.float().contiguous()
+        self.step_count += 1
+        d = self.decay_end
+        if d > 0:
+            ops.adamw_(b.params[:d], b.grads[:d], self.exp_avg[:d], self.exp_avg_sq[:d], self.w16[:d], self.lr,
+                       self.betas[0], self.betas[1], self.eps, self.wd, self.step_count, clip)
+        if d < b.total:
+            ops.adamw_(b.params[d:], b.grads[d:], self.exp_avg[d:], self.exp_avg_sq[d:], self.w16[d:], self.lr,
+                       self.betas[0], self.betas[1], self.eps, 0.0, self.step_count, clip)
+        if self.extra_opt is not None:
+            for p in self.extra:
+                if p.grad is not None:
+                    p.grad.mul_(clip)
+            self.extra_opt.step()
+        return norm
+
+    def close(self):
+        self.bucket.remove_hooks()
