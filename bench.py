@@ -195,12 +195,27 @@ def cpu_oracle_step(orc, trainable, batch):
         t.grad = None
     out = orc.forward(batch["vision_x"], batch["lang_x"], attention_mask=batch["attention_mask"], labels=batch["labels"])
     out.loss.backward()
-    return float(out.loss)
+    return float(out.loss.detach())
+
+
+def usable_cores():
+    """Host cores this process may actually use: affinity mask capped by the cgroup CPU quota."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except Exception:
+        pass
+    return n
 
 
 def time_cpu_oracle(model_name, sample_batch, t_img, t_txt, steps, warmup):
     from open_flamingo_b200.testing import synthetic_batch
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     orc, trainable, media_id, eoc_id, vocab, image_size = build_cpu_oracle(model_name)
     batch = synthetic_batch(sample_batch, t_img, t_txt, media_id, eoc_id, vocab, image_size=image_size, seed=1)

@@ -307,6 +307,178 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 }
 
 // ----------------------------------------------------------------------------------------------
+// 2-CTA variant: a cluster of two CTAs (one SM pair) owns a 256 x 256 output tile.  Each CTA stages its own
+// 128 rows of A and 128 rows of B (half the B traffic per SM of the 1-CTA kernel, so the shared-memory port
+// no longer caps the tensor pipe); the leader CTA's MMA thread issues tcgen05.mma.cta_group::2 (M = 256) and
+// each CTA's TMEM receives its own 128 accumulator rows, drained by its own epilogue warps.
+struct Smem2 {
+  static constexpr int A_BYTES = BM * BK * 2;        // 16 KiB : this CTA's 128 rows of A
+  static constexpr int B_BYTES = 128 * BK * 2;       // 16 KiB : this CTA's 128 rows of B
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = 6;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+};
+
+template <int A_MN, int B_MN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+             const GemmParams p) {
+  using L = Smem2;
+  constexpr int STAGES = L::STAGES;
+  constexpr int BN2 = 256;
+  constexpr uint32_t TMEM_COLS = 2 * BN2;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+
+  const int m_tiles = (p.M + 255) / 256;
+  const int n_tiles = (p.N + BN2 - 1) / BN2;
+  const int num_work = m_tiles * n_tiles * p.splits;
+  const int total_kb = (p.K + BK - 1) / BK;
+  const int first_work = (int)cluster_id_x();
+  const int work_stride = (int)num_clusters_x();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }  // 4 warps x 2 CTAs
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2cta(tmem_ptr, TMEM_COLS);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // peer barriers are initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one thread per CTA) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int w = first_work; w < num_work; w += work_stride) {
+        const int mt = w % m_tiles;
+        const int rest = w / m_tiles;
+        const int nt = rest % n_tiles;
+        const int ks = rest / n_tiles;
+        const int m0 = mt * 256 + (int)cta_rank * 128;
+        const int n0 = nt * BN2 + (int)cta_rank * 128;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(total_kb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);  // both CTAs' bytes land here
+          const int k0 = kb * BK;
+          if constexpr (A_MN == 0) {
+            tma_load_2d_2cta(sa, &tma_a, &full_bar[stage], k0, m0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) tma_load_2d_2cta(sa + i * (BK * 128), &tma_a, &full_bar[stage], m0 + 64 * i, k0);
+          }
+          if constexpr (B_MN == 0) {
+            tma_load_2d_2cta(sb, &tma_b, &full_bar[stage], k0, n0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) tma_load_2d_2cta(sb + i * (BK * 128), &tma_b, &full_bar[stage], n0 + 64 * i, k0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread of the leader CTA) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN2, A_MN, B_MN);
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aphase = 0;
+      for (int w = first_work; w < num_work; w += work_stride) {
+        const int ks = (w / m_tiles) / n_tiles;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(total_kb, kb0 + p.kb_per_split);
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN2;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t adesc = A_MN ? make_smem_desc_sw128(sa + k * 2048, BK * 128, 1024)
+                                        : make_smem_desc_sw128(sa + k * 32, 0, 1024);
+            const uint64_t bdesc = B_MN ? make_smem_desc_sw128(sb + k * 2048, BK * 128, 1024)
+                                        : make_smem_desc_sw128(sb + k * 32, 0, 1024);
+            umma_bf16_2cta(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_2cta(&empty_bar[stage]);   // frees this stage in BOTH CTAs
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2cta(&tmem_full[as]);        // accumulator ready in BOTH CTAs
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= EPI_WARP0) {
+    // ===================== epilogue (4 warps per CTA; this CTA's 128 rows) =====================
+    const int q = warp - EPI_WARP0;
+    float gate_t = 1.0f;
+    if constexpr (EPI == OFK_EPI_GATE_RESID_F32) {
+      if (p.gate != nullptr) gate_t = tanhf(__ldg(p.gate));
+    }
+    int as = 0; uint32_t aphase = 0;
+    for (int w = first_work; w < num_work; w += work_stride) {
+      const int mt = w % m_tiles;
+      const int nt = (w / m_tiles) % n_tiles;
+      const int row = mt * 256 + (int)cta_rank * 128 + q * 32 + lane;
+      const int n0 = nt * BN2;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN2;
+#pragma unroll 2
+      for (int c = 0; c < BN2 / 16; ++c) {
+        uint32_t acc[16];
+        tmem_ld16(taddr + c * 16, acc);
+        tmem_ld_wait();
+        const int col = n0 + c * 16;
+        if (row < p.M && col < p.N) epilogue16<EPI>(p, gate_t, row, col, acc);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tmem_empty[as], 0);   // the leader's MMA thread waits for all 8 warps
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // neither CTA may free TMEM / exit while its peer can still touch it
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, TMEM_COLS);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
 // Host side: tensor-map cache + dispatch.
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -401,6 +573,51 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
   return 0;
 }
 
+template <int A_MN, int B_MN, int EPI>
+static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  auto kern = gemm2_kernel<A_MN, B_MN, EPI>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2::TOTAL);
+    if (e != cudaSuccess) return ofk_set_error(OFK_ERR_CUDA, cudaGetErrorString(e));
+    attr_done = true;
+  }
+  const int work = ((p.M + 255) / 256) * ((p.N + 255) / 256) * p.splits;
+  int clusters = g_num_sms / 2;
+  if (work < clusters) clusters = work;
+  kern<<<2 * clusters, NUM_THREADS, Smem2::TOTAL, stream>>>(ta, tb, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return ofk_set_error(OFK_ERR_CUDA, cudaGetErrorString(e));
+  ofk_count_launch();
+  return 0;
+}
+
+template <int EPI>
+static int dispatch_major2(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                           cudaStream_t s) {
+  if (a_mn == 0 && b_mn == 0) return launch2<0, 0, EPI>(ta, tb, p, s);
+  if (a_mn == 0 && b_mn == 1) return launch2<0, 1, EPI>(ta, tb, p, s);
+  if (a_mn == 1 && b_mn == 1) return launch2<1, 1, EPI>(ta, tb, p, s);
+  return launch2<1, 0, EPI>(ta, tb, p, s);
+}
+
+static int dispatch_epi2(int epi, int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb,
+                         const GemmParams& p, cudaStream_t s) {
+  switch (epi) {
+    case OFK_EPI_STORE_BF16: return dispatch_major2<OFK_EPI_STORE_BF16>(a_mn, b_mn, ta, tb, p, s);
+    case OFK_EPI_STORE_F32: return dispatch_major2<OFK_EPI_STORE_F32>(a_mn, b_mn, ta, tb, p, s);
+    case OFK_EPI_ATOMIC_F32: return dispatch_major2<OFK_EPI_ATOMIC_F32>(a_mn, b_mn, ta, tb, p, s);
+    case OFK_EPI_BIAS_BF16: return dispatch_major2<OFK_EPI_BIAS_BF16>(a_mn, b_mn, ta, tb, p, s);
+    case OFK_EPI_BIAS_QGELU_BF16: return dispatch_major2<OFK_EPI_BIAS_QGELU_BF16>(a_mn, b_mn, ta, tb, p, s);
+    case OFK_EPI_GELU_DUAL: return dispatch_major2<OFK_EPI_GELU_DUAL>(a_mn, b_mn, ta, tb, p, s);
+    case OFK_EPI_GATE_RESID_F32: return dispatch_major2<OFK_EPI_GATE_RESID_F32>(a_mn, b_mn, ta, tb, p, s);
+    case OFK_EPI_DGELU_BF16: return dispatch_major2<OFK_EPI_DGELU_BF16>(a_mn, b_mn, ta, tb, p, s);
+    case OFK_EPI_BIAS_RESID_F32: return dispatch_major2<OFK_EPI_BIAS_RESID_F32>(a_mn, b_mn, ta, tb, p, s);
+    case OFK_EPI_BIAS_GELU_BF16: return dispatch_major2<OFK_EPI_BIAS_GELU_BF16>(a_mn, b_mn, ta, tb, p, s);
+  }
+  return ofk_set_error(OFK_ERR_ARG, "unknown GEMM epilogue");
+}
+
 template <int BN, int EPI>
 static int dispatch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                           cudaStream_t s) {
@@ -453,6 +670,8 @@ extern "C" int ofk_gemm_bf16(int epi, int a_mn_major, int b_mn_major, const void
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (g_num_sms <= 0) return ofk_set_error(OFK_ERR_CUDA, "no CUDA device");
   }
+  // block_n: 0 = auto, 128 / 256 = 1-CTA tile width, 512 = force the 2-CTA (256 x 256 per SM pair) kernel
+  const bool two_cta = block_n == 512 || (block_n == 0 && M >= 512 && N >= 256);
   const int BN = (block_n == 128 || block_n == 256) ? block_n : ((N % 256 == 0 || N > 1024) ? 256 : 128);
   const int total_kb = (K + BK - 1) / BK;
   if (splits > total_kb) splits = total_kb;
@@ -464,6 +683,13 @@ extern "C" int ofk_gemm_bf16(int epi, int a_mn_major, int b_mn_major, const void
 
   CUtensorMap ta, tb;
   int rc;
+  if (two_cta) {
+    rc = a_mn_major ? get_tensor_map(A, lda, K, M, 64, BK, &ta) : get_tensor_map(A, lda, M, K, BK, 128, &ta);
+    if (rc) return rc;
+    rc = b_mn_major ? get_tensor_map(B, ldb, K, N, 64, BK, &tb) : get_tensor_map(B, ldb, N, K, BK, 128, &tb);
+    if (rc) return rc;
+    return dispatch_epi2(epi, a_mn_major, b_mn_major, ta, tb, p, stream);
+  }
   // K-major: tensor [rows, K], box {64 (k), tile rows}. MN-major: tensor [K, rows], box {64 (rows), 64 (k)}.
   rc = a_mn_major ? get_tensor_map(A, lda, K, M, 64, BK, &ta) : get_tensor_map(A, lda, M, K, BK, BM, &ta);
   if (rc) return rc;

