@@ -29,8 +29,9 @@ namespace ofk {
 constexpr int BM = 128;       // UMMA_M (cta_group::1)
 constexpr int BK = 64;        // one 128-byte swizzle atom of bf16
 constexpr int UMMA_K = 16;    // fixed for 16-bit inputs
-constexpr int NUM_THREADS = 256;
-constexpr int EPI_WARP0 = 4;  // warps 4..7 are the epilogue (warp % 4 == TMEM lane quarter)
+constexpr int EPI_WARP0 = 4;      // warps 4..11 are the epilogue: TMEM lane quarter = warp % 4, column half = (warp-4)/4
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = (EPI_WARP0 + NUM_EPI_WARPS) * 32;
 
 struct GemmParams {
   int M, N, K;
@@ -181,7 +182,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], NUM_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -268,8 +269,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }
     __syncwarp();
   } else if (warp >= EPI_WARP0) {
-    // ===================== epilogue (4 warps; TMEM -> regs -> fused op -> global) =====================
-    const int q = warp - EPI_WARP0;  // TMEM lane quarter == warp % 4
+    // ===================== epilogue (8 warps; TMEM -> regs -> fused op -> global) =====================
+    const int q = warp & 3;                    // TMEM lane quarter == warp % 4
+    const int half = (warp - EPI_WARP0) >> 2;  // which half of the tile's columns this warp drains
     float gate_t = 1.0f;
     if constexpr (EPI == OFK_EPI_GATE_RESID_F32) {
       if (p.gate != nullptr) gate_t = tanhf(__ldg(p.gate));
@@ -282,14 +284,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const int n0 = nt * BN;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
-#pragma unroll 2
-      for (int c = 0; c < BN / 16; ++c) {
-        uint32_t acc[16];
-        tmem_ld16(taddr + c * 16, acc);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + half * (BN / 2);
+#pragma unroll 1
+      for (int c = 0; c < BN / 64; ++c) {      // 32 columns per iteration: two TMEM loads in flight per wait
+        uint32_t acc0[16], acc1[16];
+        tmem_ld16(taddr + c * 32, acc0);
+        tmem_ld16(taddr + c * 32 + 16, acc1);
         tmem_ld_wait();
-        const int col = n0 + c * 16;
-        if (row < p.M && col < p.N) epilogue16<EPI>(p, gate_t, row, col, acc);
+        const int col = n0 + half * (BN / 2) + c * 32;
+        if (row < p.M && col < p.N) epilogue16<EPI>(p, gate_t, row, col, acc0);
+        if (row < p.M && col + 16 < p.N) epilogue16<EPI>(p, gate_t, row, col + 16, acc1);
       }
       tc_fence_before();
       __syncwarp();
@@ -355,7 +359,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }  // 4 warps x 2 CTAs
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 2 * NUM_EPI_WARPS); }  // both CTAs' warps
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -439,8 +443,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     }
     __syncwarp();
   } else if (warp >= EPI_WARP0) {
-    // ===================== epilogue (4 warps per CTA; this CTA's 128 rows) =====================
-    const int q = warp - EPI_WARP0;
+    // ===================== epilogue (8 warps per CTA; this CTA's 128 rows) =====================
+    const int q = warp & 3;
+    const int half = (warp - EPI_WARP0) >> 2;
     float gate_t = 1.0f;
     if constexpr (EPI == OFK_EPI_GATE_RESID_F32) {
       if (p.gate != nullptr) gate_t = tanhf(__ldg(p.gate));
@@ -453,18 +458,20 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
       const int n0 = nt * BN2;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN2;
-#pragma unroll 2
-      for (int c = 0; c < BN2 / 16; ++c) {
-        uint32_t acc[16];
-        tmem_ld16(taddr + c * 16, acc);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN2 + half * (BN2 / 2);
+#pragma unroll 1
+      for (int c = 0; c < BN2 / 64; ++c) {
+        uint32_t acc0[16], acc1[16];
+        tmem_ld16(taddr + c * 32, acc0);
+        tmem_ld16(taddr + c * 32 + 16, acc1);
         tmem_ld_wait();
-        const int col = n0 + c * 16;
-        if (row < p.M && col < p.N) epilogue16<EPI>(p, gate_t, row, col, acc);
+        const int col = n0 + half * (BN2 / 2) + c * 32;
+        if (row < p.M && col < p.N) epilogue16<EPI>(p, gate_t, row, col, acc0);
+        if (row < p.M && col + 16 < p.N) epilogue16<EPI>(p, gate_t, row, col + 16, acc1);
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(&tmem_empty[as], 0);   // the leader's MMA thread waits for all 8 warps
+      if (lane == 0) mbar_arrive_cluster(&tmem_empty[as], 0);   // the leader's MMA thread waits for all 16 warps
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   }
