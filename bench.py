@@ -41,6 +41,9 @@ def parse_args():
     ap.add_argument("--t_txt", type=int, default=256)
     ap.add_argument("--model", default="of3b", choices=["of3b", "of9b", "tiny"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lm", default="fused", choices=["fused", "eager"],
+                    help="frozen-LM decoder blocks: 'fused' = libofk kernels (lm_blocks.py), 'eager' = HF PyTorch "
+                         "modules as in the reference")
     ap.add_argument("--cpu-sample-batch", type=int, default=1)
     return ap.parse_args()
 
@@ -261,6 +264,8 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
+    from open_flamingo_b200 import lm_blocks
+    lm_blocks.ENABLED = args.lm == "fused"
     vit_cfg, mpt_kw, every = model_dims(args.model)
     import contextlib
     import io
@@ -364,7 +369,7 @@ def run_ours(args):
                 "config": {"workload": f"{args.model.upper()} (ViT-L/14 + MPT-1B-shaped HF MptForCausalLM, xattn_every={every}) "
                                        "amp_bf16 train step: fwd+bwd+grad all-reduce+clip+AdamW",
                            "global_batch": world * B, "per_gpu_batch": B, "t_img": T_img, "seq_len": T_txt,
-                           "parallelism": f"dp{world}", "l2": "per-step working set (>10 GB weights+activations) exceeds the 126 MB L2; no explicit flush",
+                           "parallelism": f"dp{world}", "frozen_lm_blocks": args.lm, "l2": "per-step working set (>10 GB weights+activations) exceeds the 126 MB L2; no explicit flush",
                            "trainable_params": sum(p.numel() for p in model.parameters() if p.requires_grad)},
                 "e2e": {"value": tokens / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},

@@ -118,6 +118,31 @@ int ofk_attn_bwd(const void* q, const void* k, const void* v, const void* o, con
                  int mask_mode, const int* text_time, int keys_per_media, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Dense self-attention core of the frozen LM's decoder blocks (HF MptAttention; reached via
+ * flamingo_lm.py:63-65 -- SURVEY.md section 8f rank 1).  head_dim 64 or 128.
+ *   S = scale * Q K^T + slopes[h] * key_index  (ALiBi; slopes NULL = no bias)
+ *   masked (mask[b, q, k] != 0, mask: [batch, nq, nk] bytes or NULL; and/or causal: key > query + nk - nq)
+ *   scores take "finfo.min" exactly like masked_fill: a fully masked row attends uniformly.
+ *   pure_causal_flag: optional DEVICE int; nonzero means "the mask is exactly the causal rule" (all-ones HF
+ *   attention_mask): the kernel then ignores `mask`, applies the causal rule and skips key tiles above the
+ *   diagonal -- a device-side decision, so no host synchronisation is needed to pick the fast path.
+ *   lse: [batch, heads, nq] f32, log2 domain (consumed only by ofk_attn_dense_bwd).
+ * Backward is dgrad only (the LM is frozen): dq/dk/dv bf16, fully overwritten.
+ */
+int ofk_attn_dense_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int batch, int heads,
+                       int head_dim, int nq, int nk, long long q_bstride, long long ldq, long long k_bstride,
+                       long long ldk, long long v_bstride, long long ldv, long long o_bstride, long long ldo,
+                       float scale, int causal, const unsigned char* mask, const float* slopes,
+                       const int* pure_causal_flag, void* stream);
+int ofk_attn_dense_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                       const float* lse, float* delta, void* dq, void* dk, void* dv, int batch, int heads,
+                       int head_dim, int nq, int nk, long long q_bstride, long long ldq, long long k_bstride,
+                       long long ldk, long long v_bstride, long long ldv, long long o_bstride, long long ldo,
+                       long long dq_bstride, long long lddq, long long dk_bstride, long long lddk,
+                       long long dv_bstride, long long lddv, float scale, int causal, const unsigned char* mask,
+                       const float* slopes, const int* pure_causal_flag, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Small fused elementwise / reduction kernels.
  */
 /* text_time[b, t] = inclusive cumsum over t of (ids[b,t] == media_id)   (helpers.py:208; flamingo.py:310)

@@ -162,14 +162,23 @@ __global__ void __launch_bounds__(LNB_THREADS) ln_bwd_kernel(
   }
 }
 
-__global__ void ln_bwd_reduce_kernel(const float* __restrict__ part, int nblocks, int D, float* __restrict__ dgamma,
-                                     float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;  // over 2*D
-  if (c >= 2 * D) return;
+// Column-sum of the per-block partials: 64 columns x 4 row groups per 256-thread block (coalesced 256-byte row
+// segments, 4x the parallelism of one-thread-per-column), then a shared-memory fold of the row groups.
+__global__ void __launch_bounds__(256) ln_bwd_reduce_kernel(const float* __restrict__ part, int nblocks, int D,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float s_acc[4][64];
+  const int c = blockIdx.x * 64 + (threadIdx.x & 63);  // over 2*D
+  const int rg = threadIdx.x >> 6;
   float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += part[(long long)b * 2 * D + c];
-  if (c < D) { if (dgamma) dgamma[c] += s; }
-  else if (dbeta) dbeta[c - D] += s;
+  if (c < 2 * D)
+    for (int b = rg; b < nblocks; b += 4) s += part[(long long)b * 2 * D + c];
+  s_acc[rg][threadIdx.x & 63] = s;
+  __syncthreads();
+  if (rg == 0 && c < 2 * D) {
+    s = (s_acc[0][threadIdx.x] + s_acc[1][threadIdx.x]) + (s_acc[2][threadIdx.x] + s_acc[3][threadIdx.x]);
+    if (c < D) { if (dgamma) dgamma[c] += s; }
+    else if (dbeta) dbeta[c - D] += s;
+  }
 }
 
 }  // namespace ofk
@@ -221,7 +230,7 @@ extern "C" int ofk_layernorm_bwd(const void* dy, int dy_is_f32, long long lddy, 
     ln_bwd_kernel<4><<<nblocks, LNB_THREADS, 0, s>>>(dy, dy_is_f32, lddy, rows_per_group, group_stride, group_offset, x, ldx, gamma, mean, rstd, rows, D, dx, lddx, dx_add, ldadd, part);
   OFK_CHECK_LAUNCH();
   if (dgamma || dbeta) {
-    ln_bwd_reduce_kernel<<<(2 * D + 255) / 256, 256, 0, s>>>(part, nblocks, D, dgamma, dbeta);
+    ln_bwd_reduce_kernel<<<(2 * D + 63) / 64, 256, 0, s>>>(part, nblocks, D, dgamma, dbeta);
     OFK_CHECK_LAUNCH();
   }
   return 0;

@@ -243,3 +243,52 @@ def adamw_(param, grad, exp_avg, exp_avg_sq, w_bf16, lr, beta1, beta2, eps, wd, 
 def sumsq_(x, out):
     L.check(L.lib().ofk_sumsq(x.data_ptr(), x.numel(), out.data_ptr(), L.stream_ptr()))
     return out
+
+
+def attn_dense_fwd(q, k, v, heads, head_dim, scale, *, causal=False, mask=None, slopes=None, pure_causal_flag=None,
+                   want_lse=True):
+    """Dense (LM self-attention) core: q/k/v [B, n, heads*head_dim] strided views; mask [B, nq, nk] bool/uint8
+    (True = masked); slopes [heads] f32 ALiBi slopes.  Returns (o, lse)."""
+    L.require_cuda(q, k, v)
+    B, nq, nk = q.shape[0], q.shape[1], k.shape[1]
+    out = torch.empty((B, nq, heads * head_dim), device=q.device, dtype=bf16)
+    lse = torch.empty((B, heads, nq), device=q.device, dtype=f32) if want_lse else None
+    qb, ldq = _bstride_ld(q, "q")
+    kb, ldk = _bstride_ld(k, "k")
+    vb, ldv = _bstride_ld(v, "v")
+    ob, ldo = _bstride_ld(out, "out")
+    if mask is not None and (tuple(mask.shape) != (B, nq, nk) or not mask.is_contiguous() or mask.element_size() != 1):
+        raise ValueError("mask must be a contiguous 1-byte tensor of shape [B, nq, nk]")
+    L.check(L.lib().ofk_attn_dense_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), L.ptr(lse), B, heads,
+                                       head_dim, nq, nk, qb, ldq, kb, ldk, vb, ldv, ob, ldo, scale, int(causal),
+                                       L.ptr(mask), L.ptr(slopes), L.ptr(pure_causal_flag), L.stream_ptr()))
+    return out, lse
+
+
+def attn_dense_bwd(q, k, v, o, d_o, lse, heads, head_dim, scale, *, causal=False, mask=None, slopes=None,
+                   pure_causal_flag=None, dq=None, dk=None, dv=None):
+    L.require_cuda(q, k, v, o, d_o)
+    B, nq, nk = q.shape[0], q.shape[1], k.shape[1]
+    if d_o.stride() != o.stride():
+        raise ValueError("d_o must have the same strides as o")
+    inner = heads * head_dim
+    if dq is None:
+        dq = torch.empty((B, nq, inner), device=q.device, dtype=bf16)
+    if dk is None:
+        dk = torch.empty((B, nk, inner), device=q.device, dtype=bf16)
+    if dv is None:
+        dv = torch.empty((B, nk, inner), device=q.device, dtype=bf16)
+    delta = torch.empty((B, heads, nq), device=q.device, dtype=f32)
+    qb, ldq = _bstride_ld(q, "q")
+    kb, ldk = _bstride_ld(k, "k")
+    vb, ldv = _bstride_ld(v, "v")
+    ob, ldo = _bstride_ld(o, "o")
+    dqb, lddq = _bstride_ld(dq, "dq")
+    dkb, lddk = _bstride_ld(dk, "dk")
+    dvb, lddv = _bstride_ld(dv, "dv")
+    L.check(L.lib().ofk_attn_dense_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), d_o.data_ptr(),
+                                       lse.data_ptr(), delta.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                                       B, heads, head_dim, nq, nk, qb, ldq, kb, ldk, vb, ldv, ob, ldo, dqb, lddq, dkb,
+                                       lddk, dvb, lddv, scale, int(causal), L.ptr(mask), L.ptr(slopes),
+                                       L.ptr(pure_causal_flag), L.stream_ptr()))
+    return dq, dk, dv

@@ -8,8 +8,10 @@ Interface parity with the reference's open_flamingo/src/flamingo_lm.py:
 The gated blocks are the kernel-backed ones from .helpers; the decoder blocks stay the frozen LM's own
 PyTorch modules.
 """
+import torch
 import torch.nn as nn
 
+from .. import lm_blocks
 from .helpers import GatedCrossAttentionBlock
 from .utils import getattr_recursive, setattr_recursive
 
@@ -22,6 +24,10 @@ class FlamingoLayer(nn.Module):
         self.vis_x = None
         self.media_locations = None
         self.use_cached_media = None
+        # recognised frozen decoder blocks (HF MptBlock) are evaluated on the sm_100a kernels; everything else --
+        # and every case the fast path declines -- runs the block's own PyTorch forward as in the reference
+        self._fast_block = lm_blocks.accelerate(decoder_layer)
+        self._pure_causal_flag = None
         # kept for API compatibility (train.py:368-381); the fused blocks already store only what backward needs
         if gated_cross_attn_layer is not None:
             gated_cross_attn_layer._use_gradient_checkpointing = gradient_checkpointing
@@ -49,6 +55,11 @@ class FlamingoLayer(nn.Module):
                 raise ValueError("media_locations must be conditioned before forward pass")
             lang_x = xattn(lang_x, self.vis_x, media_locations=self.media_locations,
                            use_cached_media=self.use_cached_media)
+        if self._fast_block is not None:
+            res = self._fast_block(lang_x, attention_mask=attention_mask, pure_causal_flag=self._pure_causal_flag,
+                                   **decoder_layer_kwargs)
+            if res is not None:
+                return res
         return self.decoder_layer(lang_x, attention_mask=attention_mask, **decoder_layer_kwargs)
 
 
@@ -92,10 +103,18 @@ class FlamingoLMMixin(nn.Module):
         # HF generate() feeds one token at a time after the prompt; such calls carry no <image> token and must
         # keep attending to the last cached image (flamingo_lm.py:137-146).
         use_cached = bool(self._use_cached_vision_x and self.is_conditioned() and not media_locations.any())
+        # device-side "attention_mask is all ones" flag: lets the LM attention kernel take its pure-causal fast path
+        # without a host synchronisation
+        if input_ids.is_cuda:
+            flag = torch.ones(1, dtype=torch.int32, device=input_ids.device) if attention_mask is None else \
+                attention_mask.all().to(torch.int32).reshape(1)
+        else:
+            flag = None
         for layer in self._get_decoder_layers():
             if not use_cached:
                 layer.condition_media_locations(media_locations)
             layer.condition_use_cached_media(use_cached)
+            layer._pure_causal_flag = flag
         return super().forward(input_ids=input_ids, attention_mask=attention_mask, **kwargs)
 
     def is_conditioned(self) -> bool:
