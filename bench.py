@@ -350,7 +350,7 @@ def run_ours(args):
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else \
             "fallback 1.4 PF sustained (B200_PROFILING.md)"
         achieved_tf = gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-        roofline = {"bound": "tensor", "kernel": "ofk::gemm_kernel<BN,A_MN,B_MN,EPI> (tcgen05, all variants)",
+        roofline = {"bound": "tensor", "kernel": "ofk::gemm2_kernel<A_MN,B_MN,EPI> / gemm_kernel<BN,...> (tcgen05 cta_group::2 / ::1, every launch in the timed region)",
                     "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                     "peak_source": peak_src, "traffic": None,
                     "launches_per_step": gemm_n / args.steps, "gemm_ms_per_step": gemm_ms / args.steps,

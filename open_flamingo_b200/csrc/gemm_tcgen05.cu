@@ -74,102 +74,169 @@ struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;   // 16 KiB
   static constexpr int B_BYTES = BN * BK * 2;   // 16/32 KiB
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STAGES = (BN == 256) ? 3 : 5;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + NUM_EPI_WARPS * 32 * 144 + 1024;  // + epilogue staging + slack
 };
 
 // ----------------------------------------------------------------------------------------------
-// Epilogue: 16 consecutive accumulator columns of one output row per call.
-template <int EPI>
-__device__ __forceinline__ void epilogue16(const GemmParams& p, float gate_t, int row, int col,
-                                           const uint32_t (&acc)[16]) {
-  float v[16];
+// Epilogue.  One warp drains 32 accumulator rows (lane = row) x 32 columns per round.  A lane owns a ROW, so a
+// naive "each lane stores its row" epilogue issues warp stores that touch 32 different cache lines (an ncu capture
+// showed the K=2048 GELU GEMMs pinned at 57-68 % tensor-pipe activity by exactly that L1 wavefront traffic).
+// Instead every global access goes through a per-warp shared-memory staging tile and is re-issued TRANSPOSED:
+// consecutive lanes touch consecutive 16-byte pieces of the same row (4 or 8 rows per instruction), i.e. full
+// 64/128-byte segments.  The same staging tile is used for the epilogue's reads (residual, saved pre-activation).
+constexpr int STAGE_ROW = 144;                     // 128 B payload + 16 B pad: conflict-free row-wise and piece-wise
+constexpr int STAGE_BYTES_PER_WARP = 32 * STAGE_ROW;
+constexpr int STAGING_TOTAL = NUM_EPI_WARPS * STAGE_BYTES_PER_WARP;
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// Store this warp's 32 x 32 tile (lane's row in `w`: WORDS = 32 for f32, 16 for bf16) to global, coalesced.
+// MODE 0 = plain store, 1 = red.global.add.f32 (f32 only).
+template <int ELEM_BYTES, int MODE>
+__device__ __forceinline__ void warp_store_tile(uint32_t stage, const uint32_t* w, void* gbase, long long ld, int row0,
+                                                int col0, int M, int N) {
+  constexpr int PIECES = ELEM_BYTES * 2;            // 16-byte pieces per 32-element row: 8 (f32) or 4 (bf16)
+  constexpr int EPP = 16 / ELEM_BYTES;              // elements per piece
+  const int lane = threadIdx.x & 31;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[i]);
+  for (int i = 0; i < PIECES; ++i)
+    st_shared_v4(stage + lane * STAGE_ROW + i * 16, make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]));
+  __syncwarp();
+  const int piece = lane % PIECES, rsub = lane / PIECES;
+  const int col = col0 + piece * EPP;
+#pragma unroll
+  for (int it = 0; it < PIECES; ++it) {
+    const int r = it * (32 / PIECES) + rsub;
+    const uint4 v = ld_shared_v4(stage + r * STAGE_ROW + piece * 16);
+    const int row = row0 + r;
+    if (row < M && col < N) {
+      uint8_t* g = reinterpret_cast<uint8_t*>(gbase) + ((long long)row * ld + col) * ELEM_BYTES;
+      if constexpr (MODE == 0) {
+        *reinterpret_cast<uint4*>(g) = v;
+      } else {
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g), "f"(__uint_as_float(v.x)),
+                     "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+                     : "memory");
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// Load this warp's 32 x 32 tile from global (coalesced) and hand each lane its own row in `w`.
+template <int ELEM_BYTES>
+__device__ __forceinline__ void warp_load_tile(uint32_t stage, uint32_t* w, const void* gbase, long long ld, int row0,
+                                               int col0, int M, int N) {
+  constexpr int PIECES = ELEM_BYTES * 2;
+  constexpr int EPP = 16 / ELEM_BYTES;
+  const int lane = threadIdx.x & 31;
+  const int piece = lane % PIECES, rsub = lane / PIECES;
+  const int col = col0 + piece * EPP;
+#pragma unroll
+  for (int it = 0; it < PIECES; ++it) {
+    const int r = it * (32 / PIECES) + rsub;
+    const int row = row0 + r;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (row < M && col < N)
+      v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(gbase) + ((long long)row * ld + col) * ELEM_BYTES);
+    st_shared_v4(stage + r * STAGE_ROW + piece * 16, v);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < PIECES; ++i) {
+    const uint4 v = ld_shared_v4(stage + lane * STAGE_ROW + i * 16);
+    w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void pack32_bf16(const float (&v)[32], uint32_t (&w)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+}
+
+// One round: rows [row0, row0+32) (lane = row) x columns [col0, col0+32), accumulators in `acc`.
+template <int EPI>
+__device__ __forceinline__ void epilogue32(const GemmParams& p, float gate_t, uint32_t stage, int row0, int col0,
+                                           const uint32_t (&acc)[32]) {
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
+  constexpr bool HAS_BIAS = EPI == OFK_EPI_BIAS_BF16 || EPI == OFK_EPI_BIAS_QGELU_BF16 || EPI == OFK_EPI_BIAS_GELU_BF16 ||
+                            EPI == OFK_EPI_BIAS_RESID_F32;
+  if constexpr (HAS_BIAS) {
+    // every lane needs the same 32 bias values: broadcast loads (one wavefront each)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (col0 + 4 * i < p.N) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + i);
+        v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+      }
+    }
+  }
 
   if constexpr (EPI == OFK_EPI_STORE_BF16 || EPI == OFK_EPI_BIAS_BF16 || EPI == OFK_EPI_BIAS_QGELU_BF16 ||
                 EPI == OFK_EPI_BIAS_GELU_BF16) {
-    if constexpr (EPI != OFK_EPI_STORE_BF16) {
-      const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float4 b = __ldg(b4 + i);
-        v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-      }
-    }
     if constexpr (EPI == OFK_EPI_BIAS_QGELU_BF16) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = quick_gelu(bf16_round(v[i]));
+      for (int i = 0; i < 32; ++i) v[i] = quick_gelu(bf16_round(v[i]));
     }
     if constexpr (EPI == OFK_EPI_BIAS_GELU_BF16) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = gelu_exact(bf16_round(v[i]));
+      for (int i = 0; i < 32; ++i) v[i] = gelu_exact(bf16_round(v[i]));
     }
-    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col);
-    o[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-    o[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+    uint32_t w[16];
+    pack32_bf16(v, w);
+    warp_store_tile<2, 0>(stage, w, p.out, p.ldo, row0, col0, p.M, p.N);
   } else if constexpr (EPI == OFK_EPI_STORE_F32) {
-    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    warp_store_tile<4, 0>(stage, acc, p.out, p.ldo, row0, col0, p.M, p.N);
   } else if constexpr (EPI == OFK_EPI_ATOMIC_F32) {
-    float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * i), "f"(v[4 * i]),
-                   "f"(v[4 * i + 1]), "f"(v[4 * i + 2]), "f"(v[4 * i + 3])
-                   : "memory");
-    }
+    warp_store_tile<4, 1>(stage, acc, p.out, p.ldo, row0, col0, p.M, p.N);
   } else if constexpr (EPI == OFK_EPI_GELU_DUAL) {
     // z = bf16(acc) is what the reference's Linear emits under autocast; GELU is taken of that.
-    float g[16];
+    uint32_t wz[16], wh[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { v[i] = bf16_round(v[i]); g[i] = gelu_exact(v[i]); }
-    uint4* z = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col);
-    uint4* h = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + (long long)row * p.ldo2 + col);
-    z[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-    z[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
-    h[0] = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
-    h[1] = make_uint4(pack_bf16x2(g[8], g[9]), pack_bf16x2(g[10], g[11]), pack_bf16x2(g[12], g[13]), pack_bf16x2(g[14], g[15]));
+    for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i]);
+    pack32_bf16(v, wz);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = gelu_exact(v[i]);
+    pack32_bf16(v, wh);
+    warp_store_tile<2, 0>(stage, wz, p.out, p.ldo, row0, col0, p.M, p.N);
+    warp_store_tile<2, 0>(stage, wh, p.out2, p.ldo2, row0, col0, p.M, p.N);
   } else if constexpr (EPI == OFK_EPI_GATE_RESID_F32 || EPI == OFK_EPI_BIAS_RESID_F32) {
     // out = branch * tanh(gate) + residual (fp32 residual stream); branch kept in bf16 for the gate grad.
-    if constexpr (EPI == OFK_EPI_BIAS_RESID_F32) {
-      const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+    uint32_t r[32];
+    warp_load_tile<4>(stage, r, p.aux, p.ldaux, row0, col0, p.M, p.N);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float4 b = __ldg(b4 + i);
-        v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = bf16_round(v[i]);
+    for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i]);
     if (p.out2 != nullptr) {
-      uint4* br = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + (long long)row * p.ldo2 + col);
-      br[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-      br[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+      uint32_t wb[16];
+      pack32_bf16(v, wb);
+      warp_store_tile<2, 0>(stage, wb, p.out2, p.ldo2, row0, col0, p.M, p.N);
     }
-    const float4* r4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.aux) + (long long)row * p.ldaux + col);
-    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float4 r = r4[i];
-      o[i] = make_float4(fmaf(v[4 * i], gate_t, r.x), fmaf(v[4 * i + 1], gate_t, r.y),
-                         fmaf(v[4 * i + 2], gate_t, r.z), fmaf(v[4 * i + 3], gate_t, r.w));
-    }
+    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(fmaf(v[i], gate_t, __uint_as_float(r[i])));
+    warp_store_tile<4, 0>(stage, r, p.out, p.ldo, row0, col0, p.M, p.N);
   } else if constexpr (EPI == OFK_EPI_DGELU_BF16) {
     // out = bf16( bf16(acc) * gelu'(z) ), z = saved bf16 pre-activation
-    const uint4* z4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + (long long)row * p.ldaux + col);
-    uint4 za = z4[0], zb = z4[1];
-    uint32_t zw[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
+    uint32_t z[16], w[16];
+    warp_load_tile<2>(stage, z, p.aux, p.ldaux, row0, col0, p.M, p.N);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      v[2 * i] = bf16_round(v[2 * i]) * gelu_exact_grad(bf16_lo(zw[i]));
-      v[2 * i + 1] = bf16_round(v[2 * i + 1]) * gelu_exact_grad(bf16_hi(zw[i]));
+    for (int i = 0; i < 16; ++i) {
+      v[2 * i] = bf16_round(v[2 * i]) * gelu_exact_grad(bf16_lo(z[i]));
+      v[2 * i + 1] = bf16_round(v[2 * i + 1]) * gelu_exact_grad(bf16_hi(z[i]));
     }
-    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col);
-    o[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-    o[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+    pack32_bf16(v, w);
+    warp_store_tile<2, 0>(stage, w, p.out, p.ldo, row0, col0, p.M, p.N);
   }
 }
 
@@ -300,20 +367,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
       int mt, nt, ks_unused;
       work_to_tile(w, m_tiles, n_tiles, mt, nt, ks_unused);
-      const int row = mt * BM + q * 32 + lane;
       const int n0 = nt * BN;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + half * (BN / 2);
+      const uint32_t stage_addr = smem_u32(smem + STAGES * L::STAGE_BYTES + L::BAR_BYTES) + warp * STAGE_BYTES_PER_WARP;
+      const int row0 = mt * BM + q * 32;
 #pragma unroll 1
-      for (int c = 0; c < BN / 64; ++c) {      // 32 columns per iteration: two TMEM loads in flight per wait
-        uint32_t acc0[16], acc1[16];
-        tmem_ld16(taddr + c * 32, acc0);
-        tmem_ld16(taddr + c * 32 + 16, acc1);
+      for (int c = 0; c < BN / 64; ++c) {      // 32 columns per round: two TMEM loads in flight per wait
+        uint32_t acc[32];
+        tmem_ld16(taddr + c * 32, *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));
+        tmem_ld16(taddr + c * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&acc[16]));
         tmem_ld_wait();
         const int col = n0 + half * (BN / 2) + c * 32;
-        if (row < p.M && col < p.N) epilogue16<EPI>(p, gate_t, row, col, acc0);
-        if (row < p.M && col + 16 < p.N) epilogue16<EPI>(p, gate_t, row, col + 16, acc1);
+        if (row0 < p.M && col < p.N) epilogue32<EPI>(p, gate_t, stage_addr, row0, col, acc);   // warp-uniform
       }
       tc_fence_before();
       __syncwarp();
@@ -339,9 +406,9 @@ struct Smem2 {
   static constexpr int A_BYTES = BM * BK * 2;        // 16 KiB : this CTA's 128 rows of A
   static constexpr int B_BYTES = 128 * BK * 2;       // 16 KiB : this CTA's 128 rows of B
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = 6;
+  static constexpr int STAGES = 5;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + NUM_EPI_WARPS * 32 * 144 + 1024;
 };
 
 template <int A_MN, int B_MN, int EPI>
@@ -472,20 +539,20 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     for (int w = first_work; w < num_work; w += work_stride) {
       int mt, nt, ks_unused;
       work_to_tile(w, m_tiles, n_tiles, mt, nt, ks_unused);
-      const int row = mt * 256 + (int)cta_rank * 128 + q * 32 + lane;
       const int n0 = nt * BN2;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN2 + half * (BN2 / 2);
+      const uint32_t stage_addr = smem_u32(smem + STAGES * L::STAGE_BYTES + L::BAR_BYTES) + warp * STAGE_BYTES_PER_WARP;
+      const int row0 = mt * 256 + (int)cta_rank * 128 + q * 32;
 #pragma unroll 1
       for (int c = 0; c < BN2 / 64; ++c) {
-        uint32_t acc0[16], acc1[16];
-        tmem_ld16(taddr + c * 32, acc0);
-        tmem_ld16(taddr + c * 32 + 16, acc1);
+        uint32_t acc[32];
+        tmem_ld16(taddr + c * 32, *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));
+        tmem_ld16(taddr + c * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&acc[16]));
         tmem_ld_wait();
         const int col = n0 + half * (BN2 / 2) + c * 32;
-        if (row < p.M && col < p.N) epilogue16<EPI>(p, gate_t, row, col, acc0);
-        if (row < p.M && col + 16 < p.N) epilogue16<EPI>(p, gate_t, row, col + 16, acc1);
+        if (row0 < p.M && col < p.N) epilogue32<EPI>(p, gate_t, stage_addr, row0, col, acc);   // warp-uniform
       }
       tc_fence_before();
       __syncwarp();

@@ -123,7 +123,7 @@ class GatedXattnBlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, media, media16, text_time, mask_mode, heads, n_latents, norm_w, norm_b, wq, wkv, wout,
-                attn_gate, ff_ln_w, ff_ln_b, ff_w1, ff_w2, ff_gate):
+                attn_gate, ff_ln_w, ff_ln_b, ff_w1, ff_w2, ff_gate, kv_cache=None):
         B, T, D = x.shape
         R = B * T
         inner = wq.shape[0]
@@ -135,7 +135,13 @@ class GatedXattnBlockFn(torch.autograd.Function):
         # --- masked cross attention (helpers.py:184-233)
         xn, mean, rstd = ops.layernorm_fwd(x2d, norm_w, norm_b)
         q = ops.gemm(xn, w16(wq))                                            # [R, inner]
-        kv = ops.gemm(m2d, w16(wkv))                                         # [M, 2*inner]
+        # K/V of the media are recomputed by the reference in every layer on every decode step
+        # (helpers.py:187-189); in no-grad mode they are computed once per (media, layer) and reused.
+        kv = kv_cache.get(id(wkv)) if kv_cache is not None else None
+        if kv is None:
+            kv = ops.gemm(m2d, w16(wkv))                                     # [M, 2*inner]
+            if kv_cache is not None:
+                kv_cache[id(wkv)] = kv
         kv3 = kv.view(B, M // B, 2 * inner)
         o, lse = ops.attn_fwd(q.view(B, T, inner), kv3[..., :inner], kv3[..., inner:], heads,
                               float((inner // heads) ** -0.5), mask_mode=mask_mode, text_time=text_time,
@@ -194,7 +200,7 @@ class GatedXattnBlockFn(torch.autograd.Function):
         grads = [sinks[n].result() for n in names]
         if block_backward_hook is not None:
             block_backward_hook(ctx.params)
-        return (dx.view(B, T, D) if needs[0] else None, dmedia, None, None, None, None, None, *grads)
+        return (dx.view(B, T, D) if needs[0] else None, dmedia, None, None, None, None, None, *grads, None)
 
 
 # ------------------------------------------------------------------------------------------ perceiver layer

@@ -124,7 +124,7 @@ class MediaContext:
     """Per-forward quantities shared by every gated block: the bf16 copy of the media latents and the
     text_time prefix sum (the reference recomputes both in each of its 24 layers, helpers.py:187-218)."""
 
-    __slots__ = ("media_ref", "media_version", "loc_ref", "cached", "t_txt", "media16", "text_time")
+    __slots__ = ("media_ref", "media_version", "loc_ref", "cached", "t_txt", "media16", "text_time", "kv")
 
     def matches(self, media, media_locations, use_cached_media, t_txt):
         if self.media_ref() is not media or self.media_version != media._version:
@@ -152,8 +152,17 @@ def get_media_context(media, media_locations, use_cached_media, t_txt):
     ctx.loc_ref = None if media_locations is None else weakref.ref(media_locations)
     ctx.cached = bool(use_cached_media)
     ctx.t_txt = t_txt
-    ctx.media16 = ops.cast_bf16(media.detach().reshape(B, T_img * n, Dv).float())
+    ctx.media16 = None
     ctx.text_time = None
+    # per-layer media K/V for inference: survives across decode steps of one generate() call because the media
+    # tensor object (and hence media16) is unchanged while only (media_locations, t_txt) vary
+    prev = _shared_media_ctx
+    same_media = prev is not None and prev.media_ref() is media and prev.media_version == media._version
+    ctx.kv = prev.kv if same_media else {}
+    if same_media:
+        ctx.media16 = prev.media16
+    if ctx.media16 is None:
+        ctx.media16 = ops.cast_bf16(media.detach().reshape(B, T_img * n, Dv).float())
     if media_locations is not None:
         ctx.text_time = ops.text_time(media_locations=media_locations, use_cached_media=bool(use_cached_media),
                                       t_txt=t_txt)
@@ -192,5 +201,6 @@ class GatedCrossAttentionBlock(nn.Module):
         out = fused.GatedXattnBlockFn.apply(
             x.float(), media.reshape(B, T_img * n, Dv).float(), ctx.media16, ctx.text_time, mask_mode, a.heads, n,
             a.norm.weight, a.norm.bias, a.to_q.weight, a.to_kv.weight, a.to_out.weight, self.attn_gate,
-            self.ff[0].weight, self.ff[0].bias, self.ff[1].weight, self.ff[3].weight, self.ff_gate)
+            self.ff[0].weight, self.ff[0].bias, self.ff[1].weight, self.ff[3].weight, self.ff_gate,
+            None if torch.is_grad_enabled() else ctx.kv)
         return out if out_dtype == torch.float32 else out.to(out_dtype)
