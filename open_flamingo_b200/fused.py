@@ -137,11 +137,12 @@ class GatedXattnBlockFn(torch.autograd.Function):
         q = ops.gemm(xn, w16(wq))                                            # [R, inner]
         # K/V of the media are recomputed by the reference in every layer on every decode step
         # (helpers.py:187-189); in no-grad mode they are computed once per (media, layer) and reused.
-        kv = kv_cache.get(id(wkv)) if kv_cache is not None else None
+        kv_key = (id(wkv), wkv._version)
+        kv = kv_cache.get(kv_key) if kv_cache is not None else None
         if kv is None:
             kv = ops.gemm(m2d, w16(wkv))                                     # [M, 2*inner]
             if kv_cache is not None:
-                kv_cache[id(wkv)] = kv
+                kv_cache[kv_key] = kv
         kv3 = kv.view(B, M // B, 2 * inner)
         o, lse = ops.attn_fwd(q.view(B, T, inner), kv3[..., :inner], kv3[..., inner:], heads,
                               float((inner // heads) ** -0.5), mask_mode=mask_mode, text_time=text_time,
