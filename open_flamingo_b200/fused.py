@@ -18,6 +18,8 @@ Weight gradients: if a parameter carries `_ofk_grad` (an fp32 buffer, normally a
 bucket -- see train.FlatTrainer) the wgrad GEMM accumulates straight into it and autograd receives None;
 otherwise a fresh fp32 gradient tensor is returned and autograd/DDP handle it as usual.
 """
+import weakref
+
 import torch
 
 from . import _lib as L
@@ -33,17 +35,20 @@ block_backward_hook = None
 
 
 def w16(param):
-    """bf16 operand copy of an fp32 master weight, refreshed when the parameter changes."""
+    """bf16 operand copy of an fp32 master weight, refreshed when the parameter changes.
+
+    The cache entry holds a weak reference to the parameter and is only trusted if it still points at THIS object
+    (ids, versions and device addresses are all recycled once a parameter is freed)."""
     cached = getattr(param, "_ofk_w16", None)
     if cached is not None:  # maintained by the fused AdamW kernel (train.FlatTrainer)
         return cached
     key = id(param)
     ent = _w16_cache.get(key)
     ver = param._version
-    if ent is not None and ent[0] == ver and ent[1] == param.data_ptr() and ent[2].device == param.device:
-        return ent[2]
+    if ent is not None and ent[0]() is param and ent[1] == ver and ent[2] == param.data_ptr():
+        return ent[3]
     t = ops.cast_bf16(param.detach())
-    _w16_cache[key] = (ver, param.data_ptr(), t)
+    _w16_cache[key] = (weakref.ref(param, lambda _r, k=key: _w16_cache.pop(k, None)), ver, param.data_ptr(), t)
     return t
 
 
