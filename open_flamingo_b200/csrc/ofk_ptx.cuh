@@ -218,15 +218,27 @@ __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u 
 // approximation (|abs err| < 1.5e-7, far below bf16 output resolution): one MUFU.EX2, one MUFU.RCP and 5 FMAs
 // instead of the ~30-instruction erff -- the GELU epilogues otherwise out-weigh a K=1024..2048 mainloop.
 // The Gaussian exp(-x^2/2) it needs is the same one gelu'(x) needs for the pdf term.
+// single-instruction MUFU forms (the IEEE __frcp_rn expands to a Newton fix-up with a slow-path CALL per element,
+// which serialised the epilogue: SASS showed 32 CALL + 59 BSSY in the GELU kernel)
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ void gelu_terms(float x, float& cdf, float& gauss) {
   const float au = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, au, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, au, 1.0f));
   float poly = fmaf(t, 1.061405429f, -1.453152027f);
   poly = fmaf(t, poly, 1.421413741f);
   poly = fmaf(t, poly, -0.284496736f);
   poly = fmaf(t, poly, 0.254829592f);
   poly *= t;
-  gauss = __expf(-au * au);                   // exp(-x^2 / 2)
+  gauss = ex2_approx(-1.4426950408889634f * au * au);   // exp(-x^2 / 2)
   const float half_erfc = 0.5f * poly * gauss;  // 0.5 * erfc(|x| / sqrt 2)
   cdf = x >= 0.f ? 1.0f - half_erfc : half_erfc;
 }
@@ -240,7 +252,9 @@ __device__ __forceinline__ float gelu_exact_grad(float x) {
   gelu_terms(x, cdf, g);
   return fmaf(x * 0.39894228040143268f, g, cdf);
 }
-__device__ __forceinline__ float quick_gelu(float x) { return __fdividef(x, 1.0f + __expf(-1.702f * x)); }
+__device__ __forceinline__ float quick_gelu(float x) {
+  return x * rcp_approx(1.0f + ex2_approx(-1.702f * 1.4426950408889634f * x));
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
