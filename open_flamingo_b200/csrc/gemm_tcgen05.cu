@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <unordered_map>
@@ -51,6 +52,7 @@ struct GemmParams {
   long long ldaux;
   const float* bias;
   const float* gate;
+  int stream_out;    // 1: epilogue outputs use st.global.cs (evict-first) so they do not displace the operand panels in L2
 };
 
 // Work item -> (m tile, n tile, k split).  Within a split, tiles are walked in groups of GROUP_M m-tiles by all
@@ -88,7 +90,7 @@ struct SmemLayout {
 // 64/128-byte segments.  The same staging tile is used for the epilogue's reads (residual, saved pre-activation).
 constexpr int STAGE_ROW = 144;                     // 128 B payload + 16 B pad: conflict-free row-wise and piece-wise
 constexpr int STAGE_BYTES_PER_WARP = 32 * STAGE_ROW;
-constexpr int STAGING_TOTAL = NUM_EPI_WARPS * STAGE_BYTES_PER_WARP;
+
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -101,9 +103,13 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
 
 // Store this warp's 32 x 32 tile (lane's row in `w`: WORDS = 32 for f32, 16 for bf16) to global, coalesced.
 // MODE 0 = plain store, 1 = red.global.add.f32 (f32 only).
+__device__ __forceinline__ void st_global_cs_v4(void* g, uint4 v) {
+  asm volatile("st.global.cs.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(g), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 template <int ELEM_BYTES, int MODE>
 __device__ __forceinline__ void warp_store_tile(uint32_t stage, const uint32_t* w, void* gbase, long long ld, int row0,
-                                                int col0, int M, int N) {
+                                                int col0, int M, int N, int streaming = 0) {
   constexpr int PIECES = ELEM_BYTES * 2;            // 16-byte pieces per 32-element row: 8 (f32) or 4 (bf16)
   constexpr int EPP = 16 / ELEM_BYTES;              // elements per piece
   const int lane = threadIdx.x & 31;
@@ -121,7 +127,8 @@ __device__ __forceinline__ void warp_store_tile(uint32_t stage, const uint32_t* 
     if (row < M && col < N) {
       uint8_t* g = reinterpret_cast<uint8_t*>(gbase) + ((long long)row * ld + col) * ELEM_BYTES;
       if constexpr (MODE == 0) {
-        *reinterpret_cast<uint4*>(g) = v;
+        if (streaming) st_global_cs_v4(g, v);
+        else *reinterpret_cast<uint4*>(g) = v;
       } else {
         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g), "f"(__uint_as_float(v.x)),
                      "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
@@ -196,9 +203,9 @@ __device__ __forceinline__ void epilogue32(const GemmParams& p, float gate_t, ui
     }
     uint32_t w[16];
     pack32_bf16(v, w);
-    warp_store_tile<2, 0>(stage, w, p.out, p.ldo, row0, col0, p.M, p.N);
+    warp_store_tile<2, 0>(stage, w, p.out, p.ldo, row0, col0, p.M, p.N, p.stream_out);
   } else if constexpr (EPI == OFK_EPI_STORE_F32) {
-    warp_store_tile<4, 0>(stage, acc, p.out, p.ldo, row0, col0, p.M, p.N);
+    warp_store_tile<4, 0>(stage, acc, p.out, p.ldo, row0, col0, p.M, p.N, p.stream_out);
   } else if constexpr (EPI == OFK_EPI_ATOMIC_F32) {
     warp_store_tile<4, 1>(stage, acc, p.out, p.ldo, row0, col0, p.M, p.N);
   } else if constexpr (EPI == OFK_EPI_GELU_DUAL) {
@@ -210,8 +217,8 @@ __device__ __forceinline__ void epilogue32(const GemmParams& p, float gate_t, ui
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = gelu_exact(v[i]);
     pack32_bf16(v, wh);
-    warp_store_tile<2, 0>(stage, wz, p.out, p.ldo, row0, col0, p.M, p.N);
-    warp_store_tile<2, 0>(stage, wh, p.out2, p.ldo2, row0, col0, p.M, p.N);
+    warp_store_tile<2, 0>(stage, wz, p.out, p.ldo, row0, col0, p.M, p.N, p.stream_out);
+    warp_store_tile<2, 0>(stage, wh, p.out2, p.ldo2, row0, col0, p.M, p.N, p.stream_out);
   } else if constexpr (EPI == OFK_EPI_GATE_RESID_F32 || EPI == OFK_EPI_BIAS_RESID_F32) {
     // out = branch * tanh(gate) + residual (fp32 residual stream); branch kept in bf16 for the gate grad.
     uint32_t r[32];
@@ -221,11 +228,11 @@ __device__ __forceinline__ void epilogue32(const GemmParams& p, float gate_t, ui
     if (p.out2 != nullptr) {
       uint32_t wb[16];
       pack32_bf16(v, wb);
-      warp_store_tile<2, 0>(stage, wb, p.out2, p.ldo2, row0, col0, p.M, p.N);
+      warp_store_tile<2, 0>(stage, wb, p.out2, p.ldo2, row0, col0, p.M, p.N, p.stream_out);
     }
 #pragma unroll
     for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(fmaf(v[i], gate_t, __uint_as_float(r[i])));
-    warp_store_tile<4, 0>(stage, r, p.out, p.ldo, row0, col0, p.M, p.N);
+    warp_store_tile<4, 0>(stage, r, p.out, p.ldo, row0, col0, p.M, p.N, p.stream_out);
   } else if constexpr (EPI == OFK_EPI_DGELU_BF16) {
     // out = bf16( bf16(acc) * gelu'(z) ), z = saved bf16 pre-activation
     uint32_t z[16], w[16];
@@ -236,7 +243,7 @@ __device__ __forceinline__ void epilogue32(const GemmParams& p, float gate_t, ui
       v[2 * i + 1] = bf16_round(v[2 * i + 1]) * gelu_exact_grad(bf16_hi(z[i]));
     }
     pack32_bf16(v, w);
-    warp_store_tile<2, 0>(stage, w, p.out, p.ldo, row0, col0, p.M, p.N);
+    warp_store_tile<2, 0>(stage, w, p.out, p.ldo, row0, col0, p.M, p.N, p.stream_out);
   }
 }
 
@@ -772,6 +779,12 @@ extern "C" int ofk_gemm_bf16(int epi, int a_mn_major, int b_mn_major, const void
   p.kb_per_split = (total_kb + splits - 1) / splits;
   p.splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
   p.out = out; p.ldo = ldo; p.out2 = out2; p.ldo2 = ldo2; p.aux = aux; p.ldaux = ldaux; p.bias = bias; p.gate = gate;
+  {
+    static int stream_mode = -1;   // OFK_GEMM_STREAM_OUT=0/1 overrides; default: stream when the outputs exceed ~32 MB
+    if (stream_mode < 0) { const char* e = getenv("OFK_GEMM_STREAM_OUT"); stream_mode = e ? atoi(e) + 2 : 0; }
+    if (stream_mode >= 2) p.stream_out = stream_mode - 2;
+    else p.stream_out = ((long long)M * N >= (16LL << 20)) ? 1 : 0;
+  }
 
   CUtensorMap ta, tb;
   int rc;

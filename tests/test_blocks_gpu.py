@@ -183,3 +183,51 @@ def test_error_behaviour_matches_reference():
         layer(torch.zeros(1, 4, 128, device="cuda"))                          # flamingo_lm.py:47-53
     with pytest.raises(RuntimeError):
         model.perceiver(torch.zeros(1, 1, 1, 4, 128))                         # CPU tensor: no fallback
+
+
+def test_gated_xattn_block_of9b_width_vs_oracle():
+    """BASELINE configs[3] shape class: D = 4096 (MPT-7B), media width 1024, 5 images -- fwd + input/param grads."""
+    from open_flamingo_b200.src.helpers import GatedCrossAttentionBlock
+    from oracle import flamingo_oracle as O
+    torch.manual_seed(21)
+    D, Dv, B, T, Ti, n = 4096, 1024, 2, 40, 5, 64
+    blk = GatedCrossAttentionBlock(dim=D, dim_visual=Dv)
+    with torch.no_grad():
+        blk.attn_gate.fill_(0.6)
+        blk.ff_gate.fill_(-0.4)
+    sd_cpu = {k: v.detach().clone() for k, v in blk.state_dict().items()}
+    blk = blk.cuda()
+    x = torch.randn(B, T, D)
+    media = torch.randn(B, Ti, n, Dv)
+    loc = torch.zeros(B, T, dtype=torch.bool)
+    loc[0, [2, 9, 17, 25, 33]] = True
+    loc[1, [0, 8, 16, 24, 39]] = True
+    w = torch.randn(B, T, D)
+    xg, mg = x.cuda().requires_grad_(True), media.cuda().requires_grad_(True)
+    y = blk(xg, mg, media_locations=loc.cuda())
+    (y * w.cuda()).sum().backward()
+    y_ref, g_ref, in_ref = oracle_grads(
+        lambda sd, xx, mm: (O.gated_cross_attention_block(xx, mm, sd, "", loc), w), sd_cpu, x, media)
+    cmp(y, y_ref, OUT_TOL, "9B-width y")
+    cmp(xg.grad, in_ref[0], GRAD_TOL, "9B-width dx")
+    cmp(mg.grad, in_ref[1], GRAD_TOL, "9B-width dmedia")
+    for k, p in blk.named_parameters():
+        cmp(p.grad, g_ref[k], 1e-1 if k.endswith("_gate") else GRAD_TOL, f"9B-width grad {k}")
+
+
+def test_perceiver_isolation_shape_vs_oracle():
+    """BASELINE configs[4] shape: 64 latents x 4096 visual tokens x d=1024 (one image here; fwd + grads)."""
+    from open_flamingo_b200.src.helpers import PerceiverResampler
+    from oracle import flamingo_oracle as O
+    torch.manual_seed(22)
+    m = PerceiverResampler(dim=1024, depth=2)
+    sd_cpu = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m = m.cuda()
+    x = torch.randn(1, 1, 1, 4096, 1024)
+    w = torch.randn(1, 1, 64, 1024)
+    y = m(x.cuda())
+    (y * w.cuda()).sum().backward()
+    y_ref, g_ref, _ = oracle_grads(lambda sd, xx: (O.perceiver_resampler(xx, sd), w), sd_cpu, x)
+    cmp(y, y_ref, OUT_TOL, "C5 perceiver y")
+    for k, p in m.named_parameters():
+        cmp(p.grad, g_ref[k], GRAD_TOL, f"C5 perceiver grad {k}")

@@ -1,0 +1,52 @@
+"""BASELINE configs[4]: PerceiverResampler isolation bench -- 64 latents x 4096 visual tokens x d=1024, 6 layers,
+fwd+bwd on one GPU (U = 64 images), CUDA-event timed; prints achieved TFLOP/s against SURVEY section 8d's
+algorithmic count (62.8 GFLOP/image forward; backward = 2x forward minus the media-row dgrad... which IS needed
+for norm_media's affine gradients, so 3x forward is used)."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from open_flamingo_b200 import _lib
+from open_flamingo_b200.src.helpers import PerceiverResampler
+
+U, v, D, n, depth = 64, 4096, 1024, 64, 6
+torch.manual_seed(0)
+m = PerceiverResampler(dim=D, depth=depth).cuda()
+x = torch.randn(8, 8, 1, v, D, device="cuda")
+w = torch.randn(8, 8, n, D, device="cuda")
+
+
+def step():
+    for p in m.parameters():
+        p.grad = None
+    y = m(x)
+    (y * w).sum().backward()
+
+
+for _ in range(3):
+    step()
+torch.cuda.synchronize()
+l0 = _lib.launch_count()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+iters = 5
+e0.record()
+for _ in range(iters):
+    step()
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / iters
+I = 512
+fwd_per_image = depth * (2 * n * D * I + 2 * (v + n) * D * 2 * I + 4 * 8 * n * (v + n) * 64 + 2 * n * I * D + 16 * n * D * D)
+flops = 3 * fwd_per_image * U
+peaks = {}
+try:
+    peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+except Exception:
+    pass
+peak = peaks.get("bf16_tflops", 1590.0)
+print(json.dumps({"workload": "PerceiverResampler isolation C5", "images": U, "visual_tokens": v, "dim": D, "latents": n,
+                  "depth": depth, "ms_fwd_bwd": ms, "algorithmic_TFLOP": flops / 1e12, "achieved_TFLOPs": flops / ms / 1e9,
+                  "peak_TFLOPs": peak, "frac": flops / ms / 1e9 / peak, "launches_per_step": (_lib.launch_count() - l0) / iters}))

@@ -30,7 +30,8 @@ out16 = torch.empty(M, N, device=dev, dtype=bf16)
 out16b = torch.empty(M, N, device=dev, dtype=bf16)
 out32 = torch.zeros(M, N, device=dev)
 print("K, epi, bn, us, TFLOP/s, us_per_tile_wave")
-for K in (64, 256, 512, 1024, 2048, 4096, 8192):
+KS = [int(k) for k in sys.argv[1].split(',')] if len(sys.argv) > 1 else [64, 256, 512, 1024, 2048, 4096, 8192]
+for K in KS:
     a = torch.randn(M, K, device=dev, dtype=bf16)
     b = torch.randn(N, K, device=dev, dtype=bf16)
     for bn in (256, 512):
