@@ -165,6 +165,13 @@ __device__ __forceinline__ bool key_allowed(const AttnParams& p, const RowInfo& 
   const int media = key / p.kpm + 1;
   return p.mask_mode == 1 ? (r.tt == media) : (r.tt >= media);
 }
+// Same predicate with the media index (key / kpm + 1) already known -- it is constant over an 8-key n-tile
+// (kpm % 16 == 0), so the integer division is done once per n-tile, not once per score.
+__device__ __forceinline__ bool media_allowed(const AttnParams& p, const RowInfo& r, int media) {
+  if (r.kind >= 2) return true;
+  if (r.kind == 1) return false;
+  return p.mask_mode == 1 ? (r.tt == media) : (r.tt >= media);
+}
 
 // Key range [lo, hi) (in keys) a 64-row query block needs; computed cooperatively by the CTA.
 __device__ __forceinline__ void block_key_range(const AttnParams& p, int b, int q0, int* s_red, int& lo, int& hi) {
@@ -249,29 +256,46 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const AttnParams 
     // mask + scale (log2 domain)
     const int key0 = klo + j * BKV;
     float mx_a = -INFINITY, mx_b = -INFINITY;
+    if (p.mask_mode == 0 && key0 + BKV <= p.nk) {
+      // fast path (Perceiver / ViT interior tiles): no predicate at all
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int key = key0 + i * 8 + 2 * t;
-      const bool inb0 = key < p.nk, inb1 = (key + 1) < p.nk;
-      const bool aa = key_allowed(p, ra, key), ab = key_allowed(p, rb, key);  // kpm % 16 == 0: same for key+1
-      s[i][0] = (inb0 && aa) ? (ra.kind == 2 ? 0.f : s[i][0] * sl2) : -INFINITY;
-      s[i][1] = (inb1 && aa) ? (ra.kind == 2 ? 0.f : s[i][1] * sl2) : -INFINITY;
-      s[i][2] = (inb0 && ab) ? (rb.kind == 2 ? 0.f : s[i][2] * sl2) : -INFINITY;
-      s[i][3] = (inb1 && ab) ? (rb.kind == 2 ? 0.f : s[i][3] * sl2) : -INFINITY;
-      mx_a = fmaxf(mx_a, fmaxf(s[i][0], s[i][1]));
-      mx_b = fmaxf(mx_b, fmaxf(s[i][2], s[i][3]));
+      for (int i = 0; i < 8; ++i) {
+        s[i][0] *= sl2; s[i][1] *= sl2; s[i][2] *= sl2; s[i][3] *= sl2;
+        mx_a = fmaxf(mx_a, fmaxf(s[i][0], s[i][1]));
+        mx_b = fmaxf(mx_b, fmaxf(s[i][2], s[i][3]));
+      }
+    } else {
+      const bool one_media = p.mask_mode != 0 && (p.kpm % BKV) == 0;      // all 64 keys of the tile share a media
+      int media = p.mask_mode != 0 ? key0 / p.kpm + 1 : 0;
+      bool aa = media_allowed(p, ra, media), ab = media_allowed(p, rb, media);
+      const float za = ra.kind == 2 ? 0.f : sl2, zb = rb.kind == 2 ? 0.f : sl2;  // uniform rows: S = 0
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int key = key0 + i * 8 + 2 * t;
+        if (p.mask_mode != 0 && !one_media) {
+          media = (key0 + i * 8) / p.kpm + 1;
+          aa = media_allowed(p, ra, media); ab = media_allowed(p, rb, media);
+        }
+        const bool inb0 = key < p.nk, inb1 = (key + 1) < p.nk;
+        s[i][0] = (inb0 && aa) ? s[i][0] * za : -INFINITY;
+        s[i][1] = (inb1 && aa) ? s[i][1] * za : -INFINITY;
+        s[i][2] = (inb0 && ab) ? s[i][2] * zb : -INFINITY;
+        s[i][3] = (inb1 && ab) ? s[i][3] * zb : -INFINITY;
+        mx_a = fmaxf(mx_a, fmaxf(s[i][0], s[i][1]));
+        mx_b = fmaxf(mx_b, fmaxf(s[i][2], s[i][3]));
+      }
     }
     mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 1)); mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 2));
     mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 1)); mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 2));
     const float mn_a = fmaxf(m_a, mx_a), mn_b = fmaxf(m_b, mx_b);
     const float sub_a = (mn_a == -INFINITY) ? 0.f : mn_a, sub_b = (mn_b == -INFINITY) ? 0.f : mn_b;
-    const float corr_a = exp2f(m_a - sub_a), corr_b = exp2f(m_b - sub_b);  // m = -inf -> 0
+    const float corr_a = ex2_approx(m_a - sub_a), corr_b = ex2_approx(m_b - sub_b);  // m = -inf -> 0
     m_a = mn_a; m_b = mn_b;
     float rs_a = 0.f, rs_b = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      s[i][0] = exp2f(s[i][0] - sub_a); s[i][1] = exp2f(s[i][1] - sub_a);
-      s[i][2] = exp2f(s[i][2] - sub_b); s[i][3] = exp2f(s[i][3] - sub_b);
+      s[i][0] = ex2_approx(s[i][0] - sub_a); s[i][1] = ex2_approx(s[i][1] - sub_a);
+      s[i][2] = ex2_approx(s[i][2] - sub_b); s[i][3] = ex2_approx(s[i][3] - sub_b);
       rs_a += s[i][0] + s[i][1]; rs_b += s[i][2] + s[i][3];
     }
     l_a = l_a * corr_a + rs_a; l_b = l_b * corr_b + rs_b;
@@ -325,17 +349,33 @@ __global__ void attn_delta_kernel(const AttnParams p) {
 // Recompute P (C layout, rows = queries) for one 16x64 tile given raw S = Q K^T.
 __device__ __forceinline__ void recompute_p(const AttnParams& p, float (&s)[8][4], const RowInfo& ra, const RowInfo& rb,
                                             float lse_a, float lse_b, int key0, int t) {
+  // exp(scale*s - lse) == exp2(scale*log2e*s - lse*log2e)
+  const float sl2 = p.scale * LOG2E;
+  const float za = ra.kind == 2 ? 0.f : sl2, zb = rb.kind == 2 ? 0.f : sl2;
+  const float la = lse_a * LOG2E, lb = lse_b * LOG2E;
+  if (p.mask_mode == 0 && key0 + BKV <= p.nk) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s[i][0] = ex2_approx(fmaf(s[i][0], sl2, -la)); s[i][1] = ex2_approx(fmaf(s[i][1], sl2, -la));
+      s[i][2] = ex2_approx(fmaf(s[i][2], sl2, -lb)); s[i][3] = ex2_approx(fmaf(s[i][3], sl2, -lb));
+    }
+    return;
+  }
+  const bool one_media = p.mask_mode != 0 && (p.kpm % BKV) == 0;
+  int media = p.mask_mode != 0 ? key0 / p.kpm + 1 : 0;
+  bool aa = media_allowed(p, ra, media), ab = media_allowed(p, rb, media);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int key = key0 + i * 8 + 2 * t;
+    if (p.mask_mode != 0 && !one_media) {
+      media = (key0 + i * 8) / p.kpm + 1;
+      aa = media_allowed(p, ra, media); ab = media_allowed(p, rb, media);
+    }
     const bool inb0 = key < p.nk, inb1 = (key + 1) < p.nk;
-    const bool aa = key_allowed(p, ra, key), ab = key_allowed(p, rb, key);
-    const float s0 = ra.kind == 2 ? 0.f : s[i][0] * p.scale, s1 = ra.kind == 2 ? 0.f : s[i][1] * p.scale;
-    const float s2 = rb.kind == 2 ? 0.f : s[i][2] * p.scale, s3 = rb.kind == 2 ? 0.f : s[i][3] * p.scale;
-    s[i][0] = (inb0 && aa) ? __expf(s0 - lse_a) : 0.f;
-    s[i][1] = (inb1 && aa) ? __expf(s1 - lse_a) : 0.f;
-    s[i][2] = (inb0 && ab) ? __expf(s2 - lse_b) : 0.f;
-    s[i][3] = (inb1 && ab) ? __expf(s3 - lse_b) : 0.f;
+    s[i][0] = (inb0 && aa) ? ex2_approx(fmaf(s[i][0], za, -la)) : 0.f;
+    s[i][1] = (inb1 && aa) ? ex2_approx(fmaf(s[i][1], za, -la)) : 0.f;
+    s[i][2] = (inb0 && ab) ? ex2_approx(fmaf(s[i][2], zb, -lb)) : 0.f;
+    s[i][3] = (inb1 && ab) ? ex2_approx(fmaf(s[i][3], zb, -lb)) : 0.f;
   }
 }
 
@@ -462,8 +502,10 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const AttnPar
   float dk[8][4], dv[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f; dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f; }
-  uint32_t ka[4][4], va[4][4];
   const int key_a = k0 + warp * 16 + g, key_b = key_a + 8;
+  const bool inb_ka = key_a < p.nk, inb_kb = key_b < p.nk;
+  const int media_ka = p.mask_mode != 0 ? key_a / p.kpm + 1 : 0, media_kb = p.mask_mode != 0 ? key_b / p.kpm + 1 : 0;
+  const float sl2 = p.scale * LOG2E;
 
   for (int qb = 0; qb < nqb; ++qb) {
     const int buf = qb & 1;
@@ -477,7 +519,6 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const AttnPar
       cp_async_wait<0>();
     }
     __syncthreads();
-    if (qb == 0) { load_a_frags(sK, warp * 16, ka); load_a_frags(sV, warp * 16, va); }
     {
       // skip (query block, key block) pairs the media mask rules out entirely
       int need = 0;
@@ -495,19 +536,23 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const AttnPar
     float st[8][4], dpt[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f; dpt[i][0] = dpt[i][1] = dpt[i][2] = dpt[i][3] = 0.f; }
-    mma_a_tileT(st, ka, sQ[buf]);     // S^T  = K Q^T   [16 keys x 64 queries]
-    mma_a_tileT(dpt, va, sdO[buf]);   // dP^T = V dO^T
+    {
+      uint32_t fa[4][4];              // A fragments are re-read from smem each time: keeps the kernel under 255 regs
+      load_a_frags(sK, warp * 16, fa);
+      mma_a_tileT(st, fa, sQ[buf]);     // S^T  = K Q^T   [16 keys x 64 queries]
+      load_a_frags(sV, warp * 16, fa);
+      mma_a_tileT(dpt, fa, sdO[buf]);   // dP^T = V dO^T
+    }
     float dst[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int qc = i * 8 + 2 * t + (e & 1);      // query column in this tile
-        const int key = (e & 2) ? key_b : key_a;
         RowInfo r; r.tt = s_tt[buf][qc]; r.kind = s_kind[buf][qc];
-        const bool ok = key < p.nk && key_allowed(p, r, key);
-        const float sc = r.kind == 2 ? 0.f : st[i][e] * p.scale;
-        const float pv = ok ? __expf(sc - s_lse[buf][qc]) : 0.f;
+        const bool ok = ((e & 2) ? inb_kb : inb_ka) && media_allowed(p, r, (e & 2) ? media_kb : media_ka);
+        const float z = r.kind == 2 ? 0.f : sl2;
+        const float pv = ok ? ex2_approx(fmaf(st[i][e], z, -s_lse[buf][qc] * LOG2E)) : 0.f;
         st[i][e] = pv;                                                                      // P^T
         dst[i][e] = pv * (dpt[i][e] - s_del[buf][qc]) * (r.kind == 2 ? 0.f : p.scale);     // dS^T
       }

@@ -154,6 +154,13 @@ __device__ __forceinline__ int causal_tiles(const Params& p, int q0) {
   return last_key < 0 ? 0 : min(total, last_key / BKV + 1);
 }
 
+// Tile classes for the fast paths: with no explicit mask, an in-bounds key tile entirely at or below the diagonal
+// of ALL rows this thread touches needs no per-score predicate (that is ~3/4 of the causal work at T = 256).
+__device__ __forceinline__ bool tile_unmasked(const Params& p, int key_last, int row_first) {
+  if (p.mask != nullptr || key_last >= p.nk) return false;
+  return !p.causal || key_last <= row_first + (p.nk - p.nq);
+}
+
 extern __shared__ uint8_t dyn_smem[];
 
 // ================================================================ forward
@@ -202,27 +209,39 @@ __global__ void __launch_bounds__(THREADS) fwd_kernel(const Params p_in) {
     for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
     mma_rows_x_tileT<HD>(s, sQ, warp * 16, sK[buf]);
     float mx_a = -INFINITY, mx_b = -INFINITY;
+    if (tile_unmasked(p, j * BKV + BKV - 1, q0 + warp * 16)) {
+      const float kb = slope2 * (float)(j * BKV + 2 * t);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int key = j * BKV + i * 8 + 2 * t;
-      s[i][0] = score(p, s[i][0], sl2, slope2, b, row_a, key);
-      s[i][1] = score(p, s[i][1], sl2, slope2, b, row_a, key + 1);
-      s[i][2] = score(p, s[i][2], sl2, slope2, b, row_b, key);
-      s[i][3] = score(p, s[i][3], sl2, slope2, b, row_b, key + 1);
-      mx_a = fmaxf(mx_a, fmaxf(s[i][0], s[i][1]));
-      mx_b = fmaxf(mx_b, fmaxf(s[i][2], s[i][3]));
+      for (int i = 0; i < 8; ++i) {
+        const float b0 = kb + slope2 * (float)(i * 8), b1 = b0 + slope2;
+        s[i][0] = fmaf(s[i][0], sl2, b0); s[i][1] = fmaf(s[i][1], sl2, b1);
+        s[i][2] = fmaf(s[i][2], sl2, b0); s[i][3] = fmaf(s[i][3], sl2, b1);
+        mx_a = fmaxf(mx_a, fmaxf(s[i][0], s[i][1]));
+        mx_b = fmaxf(mx_b, fmaxf(s[i][2], s[i][3]));
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int key = j * BKV + i * 8 + 2 * t;
+        s[i][0] = score(p, s[i][0], sl2, slope2, b, row_a, key);
+        s[i][1] = score(p, s[i][1], sl2, slope2, b, row_a, key + 1);
+        s[i][2] = score(p, s[i][2], sl2, slope2, b, row_b, key);
+        s[i][3] = score(p, s[i][3], sl2, slope2, b, row_b, key + 1);
+        mx_a = fmaxf(mx_a, fmaxf(s[i][0], s[i][1]));
+        mx_b = fmaxf(mx_b, fmaxf(s[i][2], s[i][3]));
+      }
     }
     mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 1)); mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 2));
     mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 1)); mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 2));
     const float mn_a = fmaxf(m_a, mx_a), mn_b = fmaxf(m_b, mx_b);
     const float sub_a = (mn_a == -INFINITY) ? 0.f : mn_a, sub_b = (mn_b == -INFINITY) ? 0.f : mn_b;
-    const float corr_a = exp2f(m_a - sub_a), corr_b = exp2f(m_b - sub_b);
+    const float corr_a = ex2_approx(m_a - sub_a), corr_b = ex2_approx(m_b - sub_b);
     m_a = mn_a; m_b = mn_b;
     float rs_a = 0.f, rs_b = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      s[i][0] = exp2f(s[i][0] - sub_a); s[i][1] = exp2f(s[i][1] - sub_a);
-      s[i][2] = exp2f(s[i][2] - sub_b); s[i][3] = exp2f(s[i][3] - sub_b);
+      s[i][0] = ex2_approx(s[i][0] - sub_a); s[i][1] = ex2_approx(s[i][1] - sub_a);
+      s[i][2] = ex2_approx(s[i][2] - sub_b); s[i][3] = ex2_approx(s[i][3] - sub_b);
       rs_a += s[i][0] + s[i][1]; rs_b += s[i][2] + s[i][3];
     }
     l_a = l_a * corr_a + rs_a; l_b = l_b * corr_b + rs_b;
@@ -325,16 +344,28 @@ __global__ void __launch_bounds__(THREADS) bwd_dq_kernel(const Params p_in) {
     for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; dpv[i][0] = dpv[i][1] = dpv[i][2] = dpv[i][3] = 0.f; }
     mma_rows_x_tileT<HD>(s, sQ, warp * 16, sK[buf]);     // S  = Q K^T
     mma_rows_x_tileT<HD>(dpv, sdO, warp * 16, sV[buf]);  // dP = dO V^T
+    if (tile_unmasked(p, j * BKV + BKV - 1, q0 + warp * 16)) {
+      const float kb = slope2 * (float)(j * BKV + 2 * t);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 8; ++i) {
+        const float b0 = kb + slope2 * (float)(i * 8), b1 = b0 + slope2;
+        s[i][0] = ex2_approx(fmaf(s[i][0], sl2, b0) - lse_a) * (dpv[i][0] - del_a) * p.scale;
+        s[i][1] = ex2_approx(fmaf(s[i][1], sl2, b1) - lse_a) * (dpv[i][1] - del_a) * p.scale;
+        s[i][2] = ex2_approx(fmaf(s[i][2], sl2, b0) - lse_b) * (dpv[i][2] - del_b) * p.scale;
+        s[i][3] = ex2_approx(fmaf(s[i][3], sl2, b1) - lse_b) * (dpv[i][3] - del_b) * p.scale;
+      }
+    } else {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int key = j * BKV + i * 8 + 2 * t + (e & 1);
-        const int row = (e & 2) ? row_b : row_a;
-        const float sc = score(p, s[i][e], sl2, slope2, b, row, key);
-        const float pv = exp2f(sc - ((e & 2) ? lse_b : lse_a));
-        const bool live = key < p.nk && !is_masked(p, b, row, key);   // masked_fill passes no gradient to the scores
-        s[i][e] = live ? pv * (dpv[i][e] - ((e & 2) ? del_b : del_a)) * p.scale : 0.f;
+      for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int key = j * BKV + i * 8 + 2 * t + (e & 1);
+          const int row = (e & 2) ? row_b : row_a;
+          const float sc = score(p, s[i][e], sl2, slope2, b, row, key);
+          const float pv = ex2_approx(sc - ((e & 2) ? lse_b : lse_a));
+          const bool live = key < p.nk && !is_masked(p, b, row, key);   // masked_fill passes no gradient to the scores
+          s[i][e] = live ? pv * (dpv[i][e] - ((e & 2) ? del_b : del_a)) * p.scale : 0.f;
+        }
       }
     }
     uint32_t dsa[4][4];
@@ -418,19 +449,36 @@ __global__ void __launch_bounds__(THREADS) bwd_dkv_kernel(const Params p_in) {
     mma_rows_x_tileT<HD>(st, sK, warp * 16, sQ[buf]);     // S^T  = K Q^T   [16 keys x 64 queries]
     mma_rows_x_tileT<HD>(dpt, sV, warp * 16, sdO[buf]);   // dP^T = V dO^T
     float dst[8][4];
+    // fast path: the whole 64 x 64 (query, key) tile is in bounds and unmasked
+    const bool fast = p.mask == nullptr && k0 + BKV <= p.nk && qb * BQ + BQ <= p.nq &&
+                      (!p.causal || k0 + BKV - 1 <= qb * BQ + (p.nk - p.nq));
+    if (fast) {
+      const float ba = slope2 * (float)key_a, bb = slope2 * (float)key_b;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 8; ++i) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int qc = i * 8 + 2 * t + (e & 1);
-        const int row = qb * BQ + qc;
-        const int key = (e & 2) ? key_b : key_a;
-        const bool inb = row < p.nq;
-        const float sc = score(p, st[i][e], sl2, slope2, b, row, key);
-        const float pv = inb ? exp2f(sc - s_lse[buf][qc]) : 0.f;
-        const bool live = inb && key < p.nk && !is_masked(p, b, row, key);
-        st[i][e] = pv;                                                   // P^T
-        dst[i][e] = live ? pv * (dpt[i][e] - s_del[buf][qc]) * p.scale : 0.f;   // dS^T
+        for (int e = 0; e < 4; ++e) {
+          const int qc = i * 8 + 2 * t + (e & 1);
+          const float pv = ex2_approx(fmaf(st[i][e], sl2, (e & 2) ? bb : ba) - s_lse[buf][qc]);
+          st[i][e] = pv;
+          dst[i][e] = pv * (dpt[i][e] - s_del[buf][qc]) * p.scale;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int qc = i * 8 + 2 * t + (e & 1);
+          const int row = qb * BQ + qc;
+          const int key = (e & 2) ? key_b : key_a;
+          const bool inb = row < p.nq;
+          const float sc = score(p, st[i][e], sl2, slope2, b, row, key);
+          const float pv = inb ? ex2_approx(sc - s_lse[buf][qc]) : 0.f;
+          const bool live = inb && key < p.nk && !is_masked(p, b, row, key);
+          st[i][e] = pv;                                                   // P^T
+          dst[i][e] = live ? pv * (dpt[i][e] - s_del[buf][qc]) * p.scale : 0.f;   // dS^T
+        }
       }
     }
     uint32_t pa[4][4], dsa[4][4];
