@@ -171,6 +171,18 @@ int ofk_patchify(const float* images, int n, int H, int W, int P, void* patches,
 int ofk_vit_assemble(const void* patch_emb, const float* class_emb, const float* pos_emb, int n, int g, int D,
                      float* tokens, void* stream);
 
+/* Shifted causal-LM cross-entropy on the LM-head logits (the loss Flamingo.forward returns with labels,
+ * flamingo.py:111-117 -> HF ForCausalLMLoss: float logits, labels shifted by one, mean over non-ignored).
+ *   logits: [rows = B*T, vocab] bf16 or f32 (ld); labels: [B, T] int64 (host-unshifted when shift_labels = 1).
+ *   fwd: lse[rows]; *loss_sum += sum(lse - logit[target]); *count += #non-ignored rows.  (caller zeroes them)
+ *   bwd: dlogits = (softmax - onehot) * (*grad_scale) / max(*count, 1) for non-ignored rows, 0 otherwise. */
+int ofk_ce_fwd(const void* logits, int logits_is_f32, long long ld, long long rows, int vocab,
+               const long long* labels, int T, int shift_labels, long long ignore_index, float* lse,
+               float* loss_sum, float* count, void* stream);
+int ofk_ce_bwd(const void* logits, int logits_is_f32, long long ld, long long rows, int vocab,
+               const long long* labels, int T, int shift_labels, long long ignore_index, const float* lse,
+               const float* grad_scale, const float* count, void* dlogits, long long ldd, void* stream);
+
 /* Fused AdamW over a flat f32 parameter / gradient buffer (train.py:392-415, train_utils.py:208-216):
  * grads are first scaled by clip_scale (global-norm clip), decoupled weight decay `wd`.
  * Also emits the bf16 operand copy for the next step's GEMMs (w_bf16 may be NULL). */

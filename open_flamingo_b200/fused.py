@@ -315,3 +315,48 @@ class FinalNormFn(torch.autograd.Function):
         dx = ops.layernorm_bwd(dy2d, x2d, w, mean, rstd, dgamma=sw.buffer(), dbeta=sb.buffer(),
                                want_dx=ctx.needs_input_grad[0])
         return (dx.view(dy.shape) if dx is not None else None), sw.result(), sb.result()
+
+
+# ------------------------------------------------------------------------------------------ causal-LM loss
+class CausalLMLossFn(torch.autograd.Function):
+    """Shifted cross-entropy over [B, T, V] logits (HF ForCausalLMLoss semantics), fused fwd / bwd kernels."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, ignore_index):
+        B, T, V = logits.shape
+        lg = logits.reshape(B * T, V)
+        if lg.stride(1) != 1:
+            lg = lg.contiguous()
+        labels = labels.to(torch.int64).contiguous()
+        lse = torch.empty(B * T, device=logits.device, dtype=f32)
+        acc = torch.zeros(2, device=logits.device, dtype=f32)          # [loss_sum, count]
+        L.check(L.lib().ofk_ce_fwd(lg.data_ptr(), int(lg.dtype == f32), lg.stride(0), B * T, V, labels.data_ptr(), T, 1,
+                                   int(ignore_index), lse.data_ptr(), acc[0:1].data_ptr(), acc[1:2].data_ptr(),
+                                   L.stream_ptr()))
+        ctx.save_for_backward(lg, labels, lse, acc)
+        ctx.meta = (B, T, V, int(ignore_index))
+        return acc[0] / acc[1]     # mean over non-ignored targets (nan when there are none, like F.cross_entropy)
+
+    @staticmethod
+    def backward(ctx, g):
+        lg, labels, lse, acc = ctx.saved_tensors
+        B, T, V, ignore_index = ctx.meta
+        d = torch.empty((B * T, V), device=lg.device, dtype=lg.dtype)
+        gs = g.reshape(1).to(f32).contiguous()
+        L.check(L.lib().ofk_ce_bwd(lg.data_ptr(), int(lg.dtype == f32), lg.stride(0), B * T, V, labels.data_ptr(), T, 1,
+                                   ignore_index, lse.data_ptr(), gs.data_ptr(), acc[1:2].data_ptr(), d.data_ptr(),
+                                   d.stride(0), L.stream_ptr()))
+        return d.view(B, T, V), None, None
+
+
+def causal_lm_loss(logits, labels, vocab_size=None, num_items_in_batch=None, ignore_index=-100, shift_labels=None,
+                   **kwargs):
+    """Drop-in for transformers' ForCausalLMLoss (`model.loss_function`).  Anything outside the plain training
+    call (pre-shifted labels, num_items_in_batch, CPU tensors, exotic dtypes) defers to the HF implementation."""
+    plain = (shift_labels is None and num_items_in_batch is None and logits.is_cuda and logits.dim() == 3 and
+             logits.dtype in (bf16, f32) and labels.shape == logits.shape[:2])
+    if not plain:
+        from transformers.loss.loss_utils import ForCausalLMLoss
+        return ForCausalLMLoss(logits, labels, vocab_size, num_items_in_batch=num_items_in_batch,
+                               ignore_index=ignore_index, shift_labels=shift_labels, **kwargs)
+    return CausalLMLossFn.apply(logits, labels.to(logits.device), ignore_index)

@@ -40,6 +40,14 @@ class Flamingo(nn.Module):
         )
         self._use_gradient_checkpointing = gradient_checkpointing
         self.perceiver._use_gradient_checkpointing = gradient_checkpointing
+        # the loss returned by forward(labels=...) is HF's shifted causal-LM cross-entropy; route it through the
+        # fused kernel pair (falls back to HF's own function for anything but the plain training call)
+        if hasattr(type(lang_encoder), "loss_function"):
+            from ..fused import causal_lm_loss
+            try:
+                lang_encoder.loss_function = causal_lm_loss
+            except Exception:
+                pass
 
     # ------------------------------------------------------------------ forward
     def forward(self, vision_x: torch.Tensor, lang_x: torch.Tensor, attention_mask: torch.Tensor = None,

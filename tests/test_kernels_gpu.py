@@ -330,3 +330,25 @@ def test_adamw_sumsq(ops):
     out = torch.zeros(1, device="cuda")
     ops.sumsq_(g, out)
     close(out, (g * g).sum().view(1), 1e-5, "sumsq")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("V", [50280, 61])
+def test_causal_lm_loss_matches_hf(dtype, V):
+    """Fused shifted cross-entropy vs transformers' ForCausalLMLoss (float logits, shift, mean over non-ignored)."""
+    from transformers.loss.loss_utils import ForCausalLMLoss
+    from open_flamingo_b200.fused import causal_lm_loss
+    torch.manual_seed(13)
+    B, T = 3, 17
+    logits = (torch.randn(B, T, V, device="cuda") * 3).to(dtype)
+    labels = torch.randint(0, V, (B, T), device="cuda")
+    labels[0, 3] = -100
+    labels[2, :5] = -100
+    a = logits.clone().requires_grad_(True)
+    b = logits.clone().requires_grad_(True)
+    ref = ForCausalLMLoss(a, labels, V)
+    got = causal_lm_loss(b, labels, V)
+    assert abs(got.item() - ref.item()) <= 1e-4 * abs(ref.item()) + 1e-5
+    (ref * 1.7).backward()
+    (got * 1.7).backward()
+    close(b.grad, a.grad, 1e-2 if dtype == torch.bfloat16 else 1e-5, "dlogits")
