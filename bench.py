@@ -41,6 +41,8 @@ def parse_args():
     ap.add_argument("--t_txt", type=int, default=256)
     ap.add_argument("--model", default="of3b", choices=["of3b", "of9b", "tiny"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", default="auto", choices=["auto", "off"],
+                    help="capture the whole training step into one CUDA graph (falls back to eager if capture fails)")
     ap.add_argument("--lm", default="fused", choices=["fused", "eager"],
                     help="frozen-LM decoder blocks: 'fused' = libofk kernels (lm_blocks.py), 'eager' = HF PyTorch "
                          "modules as in the reference")
@@ -253,7 +255,7 @@ def run_ours(args):
     import torch.distributed as dist
     from open_flamingo_b200 import _lib, ops
     from open_flamingo_b200.testing import build_flamingo, synthetic_batch
-    from open_flamingo_b200.train import FlatTrainer
+    from open_flamingo_b200.train import FlatTrainer, GraphedTrainStep
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -314,22 +316,34 @@ def run_ours(args):
     for _ in range(max(3, args.warmup)):
         train_step(resident)
     barrier()
+    l0 = _lib.launch_count()
+    train_step(resident)
+    launches = _lib.launch_count() - l0          # libofk kernels per step (a graph replays exactly these nodes)
+    graphed = None
+    if args.graph == "auto":
+        graphed = GraphedTrainStep(model, trainer, resident, warmup=1)
+        if not graphed.ok:
+            if rank == 0:
+                print(f"[bench] CUDA-graph capture unavailable, running eagerly: {graphed.error}", file=sys.stderr)
+            graphed = None
+        else:
+            for _ in range(2):
+                graphed(resident)
+    barrier()
+    run_step = (lambda batch: graphed(batch)) if graphed is not None else train_step
 
     # ---- device-resident timing (value), clocks sampled during the timed region
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    l0 = _lib.launch_count()
-    t_cpu0 = time.perf_counter()
-    ms_total = timed(lambda: train_step(resident), args.steps)
-    launches = (_lib.launch_count() - l0) / args.steps
+    ms_total = timed(lambda: run_step(resident), args.steps)
     clocks = sampler.stop() if rank == 0 else {}
     ms_step = ms_total / args.steps
     tokens = world * B * T_txt
     # host time needed to ENQUEUE one step (no sync inside): must stay well below ms_step or the GPU starves
     torch.cuda.synchronize()
     t_cpu0 = time.perf_counter()
-    train_step(resident)
+    run_step(resident)
     cpu_enqueue_ms = (time.perf_counter() - t_cpu0) * 1e3
     torch.cuda.synchronize()
 
@@ -342,8 +356,10 @@ def run_ours(args):
 
     # ---- end-to-end timing: pinned host inputs -> device every step, loss read back every step
     def e2e_step():
-        batch = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        loss = train_step(batch)
+        if graphed is not None:
+            loss = graphed(host)                 # pinned host tensors -> static device buffers (async H2D) -> replay
+        else:
+            loss = train_step({k: v.to(dev, non_blocking=True) for k, v in host.items()})
         return float(loss.item())
 
     for _ in range(2):
@@ -386,7 +402,7 @@ def run_ours(args):
                 "config": {"workload": f"{args.model.upper()} (ViT-L/14 + MPT-1B-shaped HF MptForCausalLM, xattn_every={every}) "
                                        "amp_bf16 train step: fwd+bwd+grad all-reduce+clip+AdamW",
                            "global_batch": world * B, "per_gpu_batch": B, "t_img": T_img, "seq_len": T_txt,
-                           "parallelism": f"dp{world}", "frozen_lm_blocks": args.lm, "l2": "per-step working set (>10 GB weights+activations) exceeds the 126 MB L2; no explicit flush",
+                           "parallelism": f"dp{world}", "frozen_lm_blocks": args.lm, "cuda_graph": graphed is not None, "l2": "per-step working set (>10 GB weights+activations) exceeds the 126 MB L2; no explicit flush",
                            "trainable_params": sum(p.numel() for p in model.parameters() if p.requires_grad)},
                 "e2e": {"value": tokens / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},

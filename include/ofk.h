@@ -185,10 +185,12 @@ int ofk_ce_bwd(const void* logits, int logits_is_f32, long long ld, long long ro
 
 /* Fused AdamW over a flat f32 parameter / gradient buffer (train.py:392-415, train_utils.py:208-216):
  * grads are first scaled by clip_scale (global-norm clip), decoupled weight decay `wd`.
- * Also emits the bf16 operand copy for the next step's GEMMs (w_bf16 may be NULL). */
+ * Also emits the bf16 operand copy for the next step's GEMMs (w_bf16 may be NULL).
+ * step_dev / lr_dev (optional DEVICE floats) override bias_corr1/2 (= 1 - beta^step) and lr, so that a captured
+ * CUDA graph of the training step stays valid as the step count and learning-rate schedule advance. */
 int ofk_adamw(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* w_bf16, long long n,
               float lr, float beta1, float beta2, float eps, float wd, float bias_corr1, float bias_corr2,
-              const float* clip_scale, void* stream);
+              const float* clip_scale, const float* step_dev, const float* lr_dev, void* stream);
 
 /* out[0] += sum_i x[i]^2   (global grad norm, train_utils.py:208) */
 int ofk_sumsq(const float* x, long long n, float* out, void* stream);

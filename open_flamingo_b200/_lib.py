@@ -68,7 +68,7 @@ _SIGNATURES = {
     "ofk_ce_bwd": (c_int, [c_void_p, c_int, c_ll, c_ll, c_int, c_void_p, c_int, c_int, c_ll, c_void_p, c_void_p, c_void_p,
                            c_void_p, c_ll, c_void_p]),
     "ofk_adamw": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float,
-                          c_float, c_float, c_float, c_float, c_void_p, c_void_p]),
+                          c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ofk_sumsq": (c_int, [c_void_p, c_ll, c_void_p, c_void_p]),
 }
 

@@ -146,8 +146,15 @@ __global__ void vit_assemble_kernel(const __nv_bfloat16* __restrict__ pe, const 
 // ---- fused AdamW (decoupled weight decay, torch.optim.AdamW semantics) + bf16 operand refresh
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, __nv_bfloat16* __restrict__ w16, long long n, float lr, float b1,
-                             float b2, float eps, float wd, float bc1, float bc2, const float* __restrict__ clip) {
+                             float b2, float eps, float wd, float bc1, float bc2, const float* __restrict__ clip,
+                             const float* __restrict__ step_dev, const float* __restrict__ lr_dev) {
   const float cs = clip ? __ldg(clip) : 1.0f;
+  if (step_dev) {  // device-resident step counter (CUDA-graph replays cannot bake the bias corrections in)
+    const float st = __ldg(step_dev);
+    bc1 = 1.0f - powf(b1, st);
+    bc2 = 1.0f - powf(b2, st);
+  }
+  if (lr_dev) lr = __ldg(lr_dev);
   const float step = lr / bc1;
   const float inv_sqrt_bc2 = rsqrtf(bc2);
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -254,11 +261,12 @@ extern "C" int ofk_vit_assemble(const void* patch_emb, const float* class_emb, c
 
 extern "C" int ofk_adamw(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* w_bf16, long long n,
                          float lr, float beta1, float beta2, float eps, float wd, float bias_corr1, float bias_corr2,
-                         const float* clip_scale, void* stream) {
+                         const float* clip_scale, const float* step_dev, const float* lr_dev, void* stream) {
   if (!param || !grad || !exp_avg || !exp_avg_sq) return ofk_set_error(OFK_ERR_ARG, "adamw: null pointer");
   if (n <= 0) return 0;
   adamw_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, (__nv_bfloat16*)w_bf16, n,
-                                                                    lr, beta1, beta2, eps, wd, bias_corr1, bias_corr2, clip_scale);
+                                                                    lr, beta1, beta2, eps, wd, bias_corr1, bias_corr2, clip_scale,
+                                                                    step_dev, lr_dev);
   OFK_CHECK_LAUNCH();
   return 0;
 }

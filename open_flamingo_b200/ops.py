@@ -232,12 +232,14 @@ def vit_assemble(patch_emb, class_emb, pos_emb, n, g, D):
     return tok
 
 
-def adamw_(param, grad, exp_avg, exp_avg_sq, w_bf16, lr, beta1, beta2, eps, wd, step, clip_scale=None):
-    bc1 = 1.0 - beta1 ** step
-    bc2 = 1.0 - beta2 ** step
+def adamw_(param, grad, exp_avg, exp_avg_sq, w_bf16, lr, beta1, beta2, eps, wd, step, clip_scale=None, step_dev=None,
+           lr_dev=None):
+    """step: host int (ignored when step_dev, a device float tensor holding the step count, is given)."""
+    bc1 = 1.0 - beta1 ** max(step, 1)
+    bc2 = 1.0 - beta2 ** max(step, 1)
     L.check(L.lib().ofk_adamw(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
                               L.ptr(w_bf16), param.numel(), lr, beta1, beta2, eps, wd, bc1, bc2, L.ptr(clip_scale),
-                              L.stream_ptr()))
+                              L.ptr(step_dev), L.ptr(lr_dev), L.stream_ptr()))
 
 
 def sumsq_(x, out):

@@ -183,6 +183,9 @@ class FlatTrainer:
         self.extra = [p for p in model.parameters() if p.requires_grad and id(p) not in flat_ids]
         self.extra_opt = torch.optim.AdamW(self.extra, lr=lr, betas=betas, eps=eps, weight_decay=0.0) if self.extra else None
         self.step_count = 0
+        # device-resident step counter and learning rate: a captured CUDA graph of the step stays valid as they change
+        self.step_dev = torch.zeros(1, device=b.device, dtype=torch.float32)
+        self.lr_dev = torch.full((1,), float(lr), device=b.device, dtype=torch.float32)
         self._sumsq = torch.zeros(1, device=b.device, dtype=torch.float32)
         b.install_hooks()
 
@@ -212,13 +215,15 @@ class FlatTrainer:
             torch.full_like(norm, inv_world)
         clip = clip.float().contiguous()
         self.step_count += 1
+        self.step_dev.add_(1.0)
         d = self.decay_end
         if d > 0:
             ops.adamw_(b.params[:d], b.grads[:d], self.exp_avg[:d], self.exp_avg_sq[:d], self.w16[:d], self.lr,
-                       self.betas[0], self.betas[1], self.eps, self.wd, self.step_count, clip)
+                       self.betas[0], self.betas[1], self.eps, self.wd, self.step_count, clip, self.step_dev,
+                       self.lr_dev)
         if d < b.total:
             ops.adamw_(b.params[d:], b.grads[d:], self.exp_avg[d:], self.exp_avg_sq[d:], self.w16[d:], self.lr,
-                       self.betas[0], self.betas[1], self.eps, 0.0, self.step_count, clip)
+                       self.betas[0], self.betas[1], self.eps, 0.0, self.step_count, clip, self.step_dev, self.lr_dev)
         if self.extra_opt is not None:
             for p in self.extra:
                 if p.grad is not None:
@@ -226,5 +231,59 @@ class FlatTrainer:
             self.extra_opt.step()
         return norm
 
+    def set_lr(self, lr):
+        """Learning-rate schedule hook (train.py:434-450): updates the host value and the device scalar."""
+        self.lr = float(lr)
+        self.lr_dev.fill_(float(lr))
+
     def close(self):
         self.bucket.remove_hooks()
+
+
+class GraphedTrainStep:
+    """Whole training step (zero_grad -> forward under autocast -> backward -> all-reduce -> clip -> AdamW)
+    captured ONCE into a CUDA graph and replayed: ~1.5k kernel launches per step collapse into one graph launch,
+    removing the inter-kernel launch gaps and all per-step Python/ctypes work.  Inputs are copied into static
+    device buffers before each replay.  If capture is impossible (a host synchronisation inside the LM, an
+    uncapturable collective, ...) `ok` is False and calls run the same step eagerly."""
+
+    def __init__(self, model, trainer, example_batch, autocast_dtype=torch.bfloat16, warmup=3):
+        self.model, self.trainer, self.dtype = model, trainer, autocast_dtype
+        self.static = {k: v.clone() for k, v in example_batch.items()}
+        self.ok = False
+        self.error = None
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):   # also triggers every one-time cudaFuncSetAttribute / cache fill
+                self._eager(self.static)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        try:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.loss = self._eager(self.static)
+            self.ok = True
+        except Exception as e:   # noqa: BLE001 - any capture failure means: stay eager
+            self.error = repr(e)
+            self.graph = None
+            torch.cuda.synchronize()
+
+    def _eager(self, batch):
+        self.trainer.zero_grad()
+        with torch.autocast("cuda", dtype=self.dtype):
+            out = self.model(vision_x=batch["vision_x"], lang_x=batch["lang_x"],
+                             attention_mask=batch.get("attention_mask"), labels=batch["labels"])
+        out.loss.backward()
+        self.trainer.step()
+        return out.loss.detach()
+
+    def __call__(self, batch):
+        if not self.ok:
+            return self._eager(batch)
+        for k, v in batch.items():
+            if v is not self.static[k]:
+                self.static[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.loss
