@@ -325,6 +325,8 @@ def run_ours(args):
         if not graphed.ok:
             if rank == 0:
                 print(f"[bench] CUDA-graph capture unavailable, running eagerly: {graphed.error}", file=sys.stderr)
+                if os.environ.get("OFK_DEBUG"):
+                    print(graphed.traceback, file=sys.stderr)
             graphed = None
         else:
             for _ in range(2):

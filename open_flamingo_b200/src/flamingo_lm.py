@@ -115,6 +115,17 @@ class FlamingoLMMixin(nn.Module):
                 layer.condition_media_locations(media_locations)
             layer.condition_use_cached_media(use_cached)
             layer._pure_causal_flag = flag
+        if input_ids.is_cuda and torch.cuda.is_current_stream_capturing() and type(self).__mro__[2].__name__.startswith("Mpt") \
+                and (attention_mask is None or attention_mask.dim() == 2) and kwargs.get("past_key_values") is None:
+            # CUDA-graph capture: HF's mask builder creates a device scalar from a Python float (an unpinned H2D
+            # copy, illegal while capturing).  Hand the MPT body the finished 4-D mask instead -- same content:
+            # True = masked = (key after query) | (key is padding); HF returns a 4-D mask unchanged.
+            T = input_ids.shape[1]
+            future = torch.ones(T, T, dtype=torch.bool, device=input_ids.device).triu(1)
+            m4 = future.view(1, 1, T, T).expand(input_ids.shape[0], 1, T, T)
+            if attention_mask is not None:
+                m4 = m4 | (attention_mask == 0).view(input_ids.shape[0], 1, 1, T)
+            attention_mask = m4.contiguous()
         return super().forward(input_ids=input_ids, attention_mask=attention_mask, **kwargs)
 
     def is_conditioned(self) -> bool:

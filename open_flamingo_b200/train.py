@@ -266,7 +266,9 @@ class GraphedTrainStep:
                 self.loss = self._eager(self.static)
             self.ok = True
         except Exception as e:   # noqa: BLE001 - any capture failure means: stay eager
+            import traceback
             self.error = repr(e)
+            self.traceback = traceback.format_exc()
             self.graph = None
             torch.cuda.synchronize()
 
