@@ -139,10 +139,12 @@ __device__ __forceinline__ void warp_store_tile(uint32_t stage, const uint32_t* 
   __syncwarp();
 }
 
-// Load this warp's 32 x 32 tile from global (coalesced) and hand each lane its own row in `w`.
+// Epilogue operand (residual / saved pre-activation) tile, two-phase so the global latency is hidden:
+//   aux_prefetch: coalesced global loads of this warp's 32 x 32 tile into registers (issued one round ahead)
+//   aux_commit  : registers -> staging tile -> each lane reads its own row
 template <int ELEM_BYTES>
-__device__ __forceinline__ void warp_load_tile(uint32_t stage, uint32_t* w, const void* gbase, long long ld, int row0,
-                                               int col0, int M, int N) {
+__device__ __forceinline__ void aux_prefetch(uint4 (&pre)[ELEM_BYTES * 2], const void* gbase, long long ld, int row0,
+                                             int col0, int M, int N) {
   constexpr int PIECES = ELEM_BYTES * 2;
   constexpr int EPP = 16 / ELEM_BYTES;
   const int lane = threadIdx.x & 31;
@@ -150,13 +152,19 @@ __device__ __forceinline__ void warp_load_tile(uint32_t stage, uint32_t* w, cons
   const int col = col0 + piece * EPP;
 #pragma unroll
   for (int it = 0; it < PIECES; ++it) {
-    const int r = it * (32 / PIECES) + rsub;
-    const int row = row0 + r;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    const int row = row0 + it * (32 / PIECES) + rsub;
+    pre[it] = make_uint4(0u, 0u, 0u, 0u);
     if (row < M && col < N)
-      v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(gbase) + ((long long)row * ld + col) * ELEM_BYTES);
-    st_shared_v4(stage + r * STAGE_ROW + piece * 16, v);
+      pre[it] = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(gbase) + ((long long)row * ld + col) * ELEM_BYTES);
   }
+}
+template <int ELEM_BYTES>
+__device__ __forceinline__ void aux_commit(uint32_t stage, const uint4 (&pre)[ELEM_BYTES * 2], uint32_t* w) {
+  constexpr int PIECES = ELEM_BYTES * 2;
+  const int lane = threadIdx.x & 31;
+  const int piece = lane % PIECES, rsub = lane / PIECES;
+#pragma unroll
+  for (int it = 0; it < PIECES; ++it) st_shared_v4(stage + (it * (32 / PIECES) + rsub) * STAGE_ROW + piece * 16, pre[it]);
   __syncwarp();
 #pragma unroll
   for (int i = 0; i < PIECES; ++i) {
@@ -166,6 +174,9 @@ __device__ __forceinline__ void warp_load_tile(uint32_t stage, uint32_t* w, cons
   __syncwarp();
 }
 
+template <int EPI>
+struct AuxBytes { static constexpr int value = (EPI == OFK_EPI_GATE_RESID_F32 || EPI == OFK_EPI_BIAS_RESID_F32) ? 4 : (EPI == OFK_EPI_DGELU_BF16 ? 2 : 0); };
+
 __device__ __forceinline__ void pack32_bf16(const float (&v)[32], uint32_t (&w)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
@@ -174,7 +185,7 @@ __device__ __forceinline__ void pack32_bf16(const float (&v)[32], uint32_t (&w)[
 // One round: rows [row0, row0+32) (lane = row) x columns [col0, col0+32), accumulators in `acc`.
 template <int EPI>
 __device__ __forceinline__ void epilogue32(const GemmParams& p, float gate_t, uint32_t stage, int row0, int col0,
-                                           const uint32_t (&acc)[32]) {
+                                           const uint32_t (&acc)[32], uint32_t* aux_row) {
   float v[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
@@ -221,8 +232,7 @@ __device__ __forceinline__ void epilogue32(const GemmParams& p, float gate_t, ui
     warp_store_tile<2, 0>(stage, wh, p.out2, p.ldo2, row0, col0, p.M, p.N, p.stream_out);
   } else if constexpr (EPI == OFK_EPI_GATE_RESID_F32 || EPI == OFK_EPI_BIAS_RESID_F32) {
     // out = branch * tanh(gate) + residual (fp32 residual stream); branch kept in bf16 for the gate grad.
-    uint32_t r[32];
-    warp_load_tile<4>(stage, r, p.aux, p.ldaux, row0, col0, p.M, p.N);
+    uint32_t* r = aux_row;   // this lane's 32 residual values (prefetched one round ahead)
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i]);
     if (p.out2 != nullptr) {
@@ -235,8 +245,8 @@ __device__ __forceinline__ void epilogue32(const GemmParams& p, float gate_t, ui
     warp_store_tile<4, 0>(stage, r, p.out, p.ldo, row0, col0, p.M, p.N, p.stream_out);
   } else if constexpr (EPI == OFK_EPI_DGELU_BF16) {
     // out = bf16( bf16(acc) * gelu'(z) ), z = saved bf16 pre-activation
-    uint32_t z[16], w[16];
-    warp_load_tile<2>(stage, z, p.aux, p.ldaux, row0, col0, p.M, p.N);
+    uint32_t w[16];
+    const uint32_t* z = aux_row;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       v[2 * i] = bf16_round(v[2 * i]) * gelu_exact_grad(bf16_lo(z[i]));
@@ -380,14 +390,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + half * (BN / 2);
       const uint32_t stage_addr = smem_u32(smem + STAGES * L::STAGE_BYTES + L::BAR_BYTES) + warp * STAGE_BYTES_PER_WARP;
       const int row0 = mt * BM + q * 32;
+      constexpr int AUXB = AuxBytes<EPI>::value;
+      uint4 pre[AUXB ? AUXB * 2 : 1];
+      const int colbase = n0 + half * (BN / 2);
+      if constexpr (AUXB != 0) {
+        if (row0 < p.M && colbase < p.N) aux_prefetch<AUXB>(pre, p.aux, p.ldaux, row0, colbase, p.M, p.N);
+      }
 #pragma unroll 1
       for (int c = 0; c < BN / 64; ++c) {      // 32 columns per round: two TMEM loads in flight per wait
         uint32_t acc[32];
         tmem_ld16(taddr + c * 32, *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));
         tmem_ld16(taddr + c * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&acc[16]));
+        const int col = colbase + c * 32;
+        const bool live = row0 < p.M && col < p.N;                                   // warp-uniform
+        uint32_t aux_row[AUXB ? AUXB * 8 : 1];
+        if constexpr (AUXB != 0) {
+          if (live) aux_commit<AUXB>(stage_addr, pre, aux_row);
+          if (c + 1 < BN / 64 && row0 < p.M && col + 32 < p.N)                  // next round's operand: in flight
+            aux_prefetch<AUXB>(pre, p.aux, p.ldaux, row0, col + 32, p.M, p.N);       // during this round's math+stores
+        }
         tmem_ld_wait();
-        const int col = n0 + half * (BN / 2) + c * 32;
-        if (row0 < p.M && col < p.N) epilogue32<EPI>(p, gate_t, stage_addr, row0, col, acc);   // warp-uniform
+        if (live) epilogue32<EPI>(p, gate_t, stage_addr, row0, col, acc, aux_row);
       }
       tc_fence_before();
       __syncwarp();
@@ -552,14 +575,27 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN2 + half * (BN2 / 2);
       const uint32_t stage_addr = smem_u32(smem + STAGES * L::STAGE_BYTES + L::BAR_BYTES) + warp * STAGE_BYTES_PER_WARP;
       const int row0 = mt * 256 + (int)cta_rank * 128 + q * 32;
+      constexpr int AUXB = AuxBytes<EPI>::value;
+      uint4 pre[AUXB ? AUXB * 2 : 1];
+      const int colbase = n0 + half * (BN2 / 2);
+      if constexpr (AUXB != 0) {
+        if (row0 < p.M && colbase < p.N) aux_prefetch<AUXB>(pre, p.aux, p.ldaux, row0, colbase, p.M, p.N);
+      }
 #pragma unroll 1
-      for (int c = 0; c < BN2 / 64; ++c) {
+      for (int c = 0; c < BN2 / 64; ++c) {      // 32 columns per round: two TMEM loads in flight per wait
         uint32_t acc[32];
         tmem_ld16(taddr + c * 32, *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));
         tmem_ld16(taddr + c * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&acc[16]));
+        const int col = colbase + c * 32;
+        const bool live = row0 < p.M && col < p.N;                                   // warp-uniform
+        uint32_t aux_row[AUXB ? AUXB * 8 : 1];
+        if constexpr (AUXB != 0) {
+          if (live) aux_commit<AUXB>(stage_addr, pre, aux_row);
+          if (c + 1 < BN2 / 64 && row0 < p.M && col + 32 < p.N)                  // next round's operand: in flight
+            aux_prefetch<AUXB>(pre, p.aux, p.ldaux, row0, col + 32, p.M, p.N);       // during this round's math+stores
+        }
         tmem_ld_wait();
-        const int col = n0 + half * (BN2 / 2) + c * 32;
-        if (row0 < p.M && col < p.N) epilogue32<EPI>(p, gate_t, stage_addr, row0, col, acc);   // warp-uniform
+        if (live) epilogue32<EPI>(p, gate_t, stage_addr, row0, col, acc, aux_row);
       }
       tc_fence_before();
       __syncwarp();

@@ -37,19 +37,20 @@ def test_flat_trainer_matches_torch_adamw_with_clip():
     rest = [p for n, p in named if "gated_cross_attn" not in n]
     opt = torch.optim.AdamW([{"params": decay, "weight_decay": 0.1}, {"params": rest, "weight_decay": 0.0}], lr=1e-3)
     trainer = FlatTrainer(model, lr=1e-3, weight_decay=0.1, max_grad_norm=1.0)
+    got = dict(model.named_parameters())
     for _ in range(3):
         trainer.zero_grad()
-        l1 = fwd_bwd(model, batch)
-        trainer.step()
-        opt.zero_grad(set_to_none=True)
-        l2 = fwd_bwd(ref, batch)
+        fwd_bwd(model, batch)
+        # hand the SAME gradients to the torch optimizer (Adam turns noise-level gradient differences into +-lr
+        # parameter differences, so the two optimizers must see identical inputs to be compared tightly)
+        for n, p in named:
+            p.grad = got[n].grad.detach().clone()
         torch.nn.utils.clip_grad_norm_([p for _, p in named], 1.0)
         opt.step()
-        assert abs(l1.item() - l2.item()) < 2e-2 * abs(l2.item()) + 1e-3
-    got = dict(model.named_parameters())
+        trainer.step()
     for n, p in named:
         err = (got[n].detach() - p.detach()).abs().max().item()
-        assert err <= 5e-3 * (p.detach().abs().max().item() + 1e-3), f"{n}: {err}"   # 3 bf16-gradient AdamW steps
+        assert err <= 2e-6 + 1e-5 * p.detach().abs().max().item(), f"{n}: {err}"
     # parameters keep their reference names and now live in the flat buffer
     assert got["perceiver.latents"].data_ptr() >= trainer.bucket.params.data_ptr()
 
