@@ -22,6 +22,9 @@ NVCC_FLAGS = [
 ]
 
 
+EXTRA = os.environ.get("OFK_NVCC_EXTRA", "").split()
+
+
 def _nvcc():
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
@@ -61,7 +64,7 @@ def build_library(force=False, verbose=False):
 
     def compile_one(job):
         src, obj = job
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + EXTRA + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")

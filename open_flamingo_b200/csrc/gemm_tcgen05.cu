@@ -76,9 +76,9 @@ struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;   // 16 KiB
   static constexpr int B_BYTES = BN * BK * 2;   // 16/32 KiB
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 3 : 5;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + NUM_EPI_WARPS * 32 * 144 + 1024;  // + epilogue staging + slack
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + NUM_EPI_WARPS * 32 * 128 + 1024;  // + epilogue staging + slack
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -88,8 +88,9 @@ struct SmemLayout {
 // Instead every global access goes through a per-warp shared-memory staging tile and is re-issued TRANSPOSED:
 // consecutive lanes touch consecutive 16-byte pieces of the same row (4 or 8 rows per instruction), i.e. full
 // 64/128-byte segments.  The same staging tile is used for the epilogue's reads (residual, saved pre-activation).
-constexpr int STAGE_ROW = 144;                     // 128 B payload + 16 B pad: conflict-free row-wise and piece-wise
-constexpr int STAGE_BYTES_PER_WARP = 32 * STAGE_ROW;
+constexpr int STAGE_ROW = 128;                     // unpadded 128 B rows; the 16-byte piece index is XOR-swizzled with
+constexpr int STAGE_BYTES_PER_WARP = 32 * STAGE_ROW;   // (row & 7) so row-wise and piece-wise accesses are conflict-free
+__device__ __forceinline__ uint32_t stage_off(int row, int piece) { return (uint32_t)(row * STAGE_ROW + ((piece ^ (row & 7)) << 4)); }
 
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
@@ -115,14 +116,14 @@ __device__ __forceinline__ void warp_store_tile(uint32_t stage, const uint32_t* 
   const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int i = 0; i < PIECES; ++i)
-    st_shared_v4(stage + lane * STAGE_ROW + i * 16, make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]));
+    st_shared_v4(stage + stage_off(lane, i), make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]));
   __syncwarp();
   const int piece = lane % PIECES, rsub = lane / PIECES;
   const int col = col0 + piece * EPP;
 #pragma unroll
   for (int it = 0; it < PIECES; ++it) {
     const int r = it * (32 / PIECES) + rsub;
-    const uint4 v = ld_shared_v4(stage + r * STAGE_ROW + piece * 16);
+    const uint4 v = ld_shared_v4(stage + stage_off(r, piece));
     const int row = row0 + r;
     if (row < M && col < N) {
       uint8_t* g = reinterpret_cast<uint8_t*>(gbase) + ((long long)row * ld + col) * ELEM_BYTES;
@@ -164,11 +165,11 @@ __device__ __forceinline__ void aux_commit(uint32_t stage, const uint4 (&pre)[EL
   const int lane = threadIdx.x & 31;
   const int piece = lane % PIECES, rsub = lane / PIECES;
 #pragma unroll
-  for (int it = 0; it < PIECES; ++it) st_shared_v4(stage + (it * (32 / PIECES) + rsub) * STAGE_ROW + piece * 16, pre[it]);
+  for (int it = 0; it < PIECES; ++it) st_shared_v4(stage + stage_off(it * (32 / PIECES) + rsub, piece), pre[it]);
   __syncwarp();
 #pragma unroll
   for (int i = 0; i < PIECES; ++i) {
-    const uint4 v = ld_shared_v4(stage + lane * STAGE_ROW + i * 16);
+    const uint4 v = ld_shared_v4(stage + stage_off(lane, i));
     w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
   }
   __syncwarp();
@@ -436,9 +437,12 @@ struct Smem2 {
   static constexpr int A_BYTES = BM * BK * 2;        // 16 KiB : this CTA's 128 rows of A
   static constexpr int B_BYTES = 128 * BK * 2;       // 16 KiB : this CTA's 128 rows of B
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = 5;
+#ifndef OFK_STAGES2
+#define OFK_STAGES2 6
+#endif
+  static constexpr int STAGES = OFK_STAGES2;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + NUM_EPI_WARPS * 32 * 144 + 1024;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + NUM_EPI_WARPS * 32 * 128 + 1024;
 };
 
 template <int A_MN, int B_MN, int EPI>
