@@ -26,9 +26,10 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(const float* __restrict__ x
                                                      float eps, int rows, int D, void* __restrict__ y, int y_is_f32,
                                                      long long ldy, int rpg, int gstride, int goff,
                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= rows) return;
   const int lane = threadIdx.x & 31;
-  for (int row = blockIdx.x * 4 + (threadIdx.x >> 5); row < rows; row += gridDim.x * 4) {   // grid-stride: a fixed
-  const float* xr = x + (long long)row * ldx;                                                // grid of resident CTAs
+  const float* xr = x + (long long)row * ldx;
   float4 v[NV];
   float s = 0.f;
 #pragma unroll
@@ -73,7 +74,6 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(const float* __restrict__ x
       }
     }
   }
-  }  // row loop
 }
 
 // Backward: a 256-thread block walks rows blockIdx.x, +gridDim.x, ...; thread t owns float4 column groups
@@ -99,44 +99,31 @@ __global__ void __launch_bounds__(LNB_THREADS) ln_bwd_kernel(
   }
   const float invD = 1.0f / (float)D;
   int par = 0;
-  // raw loads of one row (x fp32, dy bf16/f32 packed); issued one row ahead so they overlap the block reduction
-  float4 nx[G]; float4 ndy[G]; float4 nadd[G];
-  auto load_row = [&](int r, float4 (&ox)[G], float4 (&ody)[G]) {
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float mu = mean[r], rs = rstd[r];
     const long long yr = map_row(r, rpg, gstride, goff);
+    float4 xh[G], dyv[G];
+    float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int g = 0; g < G; ++g) {
       const int c = (g * LNB_THREADS + t) * 4;
       if (c < D) {
-        ox[g] = *reinterpret_cast<const float4*>(x + (long long)r * ldx + c);
-        if (dx_add) nadd[g] = *reinterpret_cast<const float4*>(dx_add + (long long)r * ldadd + c);
+        const float4 xv = *reinterpret_cast<const float4*>(x + (long long)r * ldx + c);
         if (dy_is_f32) {
-          ody[g] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy) + yr * lddy + c);
+          dyv[g] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy) + yr * lddy + c);
         } else {
           const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(dy) + yr * lddy + c);
-          ody[g] = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+          dyv[g] = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
         }
+        xh[g] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        const float a0 = dyv[g].x * gm[g].x, a1 = dyv[g].y * gm[g].y, a2 = dyv[g].z * gm[g].z, a3 = dyv[g].w * gm[g].w;
+        s1 += (a0 + a1) + (a2 + a3);
+        s2 += (a0 * xh[g].x + a1 * xh[g].y) + (a2 * xh[g].z + a3 * xh[g].w);
       } else {
-        ox[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-        ody[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+        xh[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+        dyv[g] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-  };
-  if ((int)blockIdx.x < rows) load_row(blockIdx.x, nx, ndy);
-  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
-    const float mu = mean[r], rs = rstd[r];
-    float4 xh[G], dyv[G], addv[G];
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const float4 xv = nx[g];
-      dyv[g] = ndy[g];
-      addv[g] = nadd[g];
-      xh[g] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-      const float a0 = dyv[g].x * gm[g].x, a1 = dyv[g].y * gm[g].y, a2 = dyv[g].z * gm[g].z, a3 = dyv[g].w * gm[g].w;
-      s1 += (a0 + a1) + (a2 + a3);
-      s2 += (a0 * xh[g].x + a1 * xh[g].y) + (a2 * xh[g].z + a3 * xh[g].w);
-    }
-    if (r + (int)gridDim.x < rows) load_row(r + gridDim.x, nx, ndy);   // next row: in flight during the reduction
     s1 = warp_sum(s1); s2 = warp_sum(s2);
     if (lane == 0) { s_red[par][warp][0] = s1; s_red[par][warp][1] = s2; }
     __syncthreads();
@@ -154,7 +141,10 @@ __global__ void __launch_bounds__(LNB_THREADS) ln_bwd_kernel(
         o.y = rs * (dyv[g].y * gm[g].y - m1 - xh[g].y * m2);
         o.z = rs * (dyv[g].z * gm[g].z - m1 - xh[g].z * m2);
         o.w = rs * (dyv[g].w * gm[g].w - m1 - xh[g].w * m2);
-        if (dx_add) { o.x += addv[g].x; o.y += addv[g].y; o.z += addv[g].z; o.w += addv[g].w; }
+        if (dx_add) {
+          const float4 a = *reinterpret_cast<const float4*>(dx_add + (long long)r * ldadd + c);
+          o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+        }
         if (dx) *reinterpret_cast<float4*>(dx + (long long)r * lddx + c) = o;
         dg[g].x += dyv[g].x * xh[g].x; dg[g].y += dyv[g].y * xh[g].y; dg[g].z += dyv[g].z * xh[g].z; dg[g].w += dyv[g].w * xh[g].w;
         db[g].x += dyv[g].x; db[g].y += dyv[g].y; db[g].z += dyv[g].z; db[g].w += dyv[g].w;
@@ -202,8 +192,7 @@ extern "C" int ofk_layernorm_fwd(const float* x, long long ldx, const float* gam
   if (D <= 0 || D % 4 != 0 || D > 4096) return ofk_set_error(OFK_ERR_ARG, "layernorm: D must be a multiple of 4, <= 4096");
   if (ldx % 4 != 0 || ldy % 4 != 0) return ofk_set_error(OFK_ERR_ALIGN, "layernorm: row strides must be multiples of 4");
   cudaStream_t s = (cudaStream_t)stream_;
-  int grid = (rows + 3) / 4;
-  if (grid > 148 * 12) grid = 148 * 12;   // resident CTAs loop over rows: no partial last wave
+  const int grid = (rows + 3) / 4;
   if (D <= 1024)
     ln_fwd_kernel<8><<<grid, 128, 0, s>>>(x, ldx, gamma, beta, eps, rows, D, y, y_is_f32, ldy, rows_per_group, group_stride, group_offset, mean, rstd);
   else if (D <= 2048)
