@@ -414,7 +414,17 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tear down in a hang-proof order: release the captured graph (it holds NCCL kernels) before touching the
+        # communicator, synchronise, and leave without running NCCL's destructor-time collectives.
+        graphed = None
+        torch.cuda.synchronize()
+        try:
+            dist.barrier()
+        except Exception:
+            pass
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
