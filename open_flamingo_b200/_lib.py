@@ -90,8 +90,6 @@ def lib():
                 "(nvcc, sm_100a).  There is no CPU/PyTorch fallback for the hot path.")
         L = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in _SIGNATURES.items():
-            if os.environ.get("OFK_BRINGUP_PARTIAL") and not hasattr(L, name):
-                continue  # bring-up only: partial library
             fn = getattr(L, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
