@@ -8,7 +8,6 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include <stdlib.h>
 
 #include "ofk_internal.h"
 #include "ofk_ptx.cuh"
@@ -182,206 +181,6 @@ __global__ void __launch_bounds__(256) ln_bwd_reduce_kernel(const float* __restr
   }
 }
 
-
-// ================================================================ streaming variants (TMA bulk copies + mbarrier ring)
-// The register-resident kernels above reach only ~50 % of HBM peak in isolation: their loads are issued in one
-// burst per row and nothing is in flight while a row is reduced and written back.  Here every warp owns a small
-// shared-memory ring of rows filled by 1-D bulk copies (cp.async.bulk, completion on an mbarrier) issued NS rows
-// ahead, so each SM keeps a steady ~100 KB of loads in flight independent of the arithmetic.
-constexpr int LNS_WARPS = 4;
-
-template <int NV>
-__global__ void __launch_bounds__(LNS_WARPS * 32) ln_fwd_stream_kernel(
-    const float* __restrict__ x, long long ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
-    float eps, int rows, int D, void* __restrict__ y, int y_is_f32, long long ldy, int rpg, int gstride, int goff,
-    float* __restrict__ mean_out, float* __restrict__ rstd_out, int NS) {
-  extern __shared__ __align__(128) uint8_t lns_smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t row_bytes = (uint32_t)D * 4u;
-  float* ring = reinterpret_cast<float*>(lns_smem) + (size_t)warp * NS * D;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(lns_smem + (size_t)LNS_WARPS * NS * row_bytes) + warp * NS;
-  const int gw = blockIdx.x * LNS_WARPS + warp, tw = gridDim.x * LNS_WARPS;
-  if (lane == 0) {
-    for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
-    fence_barrier_init();
-    for (int s = 0; s < NS; ++s) {
-      const long long r = (long long)gw + (long long)s * tw;
-      if (r < rows) {
-        mbar_arrive_expect_tx(&bars[s], row_bytes);
-        bulk_load_1d(ring + (size_t)s * D, x + r * ldx, row_bytes, &bars[s]);
-      }
-    }
-  }
-  __syncwarp();
-  int it = 0;
-  for (long long row = gw; row < rows; row += tw, ++it) {
-    const int s = it % NS;
-    mbar_wait(&bars[s], (uint32_t)((it / NS) & 1));
-    const float4* src = reinterpret_cast<const float4*>(ring + (size_t)s * D);
-    float4 v[NV];
-    float sum = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c4 = i * 32 + lane;
-      if (c4 * 4 < D) { v[i] = src[c4]; sum += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
-      else v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    __syncwarp();   // every lane has its copy: the slot may be refilled
-    if (lane == 0) {
-      const long long rn = row + (long long)NS * tw;
-      if (rn < rows) {
-        mbar_arrive_expect_tx(&bars[s], row_bytes);
-        bulk_load_1d(ring + (size_t)s * D, x + rn * ldx, row_bytes, &bars[s]);
-      }
-    }
-    const float mean = warp_sum(sum) / (float)D;
-    float sq = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      if ((i * 32 + lane) * 4 < D) {
-        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-        sq += (a * a + b * b) + (c * c + d * d);
-      }
-    }
-    const float rstd = rsqrtf(warp_sum(sq) / (float)D + eps);
-    if (lane == 0) {
-      if (mean_out) mean_out[row] = mean;
-      if (rstd_out) rstd_out[row] = rstd;
-    }
-    const long long orow = map_row((int)row, rpg, gstride, goff);
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = (i * 32 + lane) * 4;
-      if (c < D) {
-        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
-        const float o0 = (v[i].x - mean) * rstd * g.x + b.x, o1 = (v[i].y - mean) * rstd * g.y + b.y;
-        const float o2 = (v[i].z - mean) * rstd * g.z + b.z, o3 = (v[i].w - mean) * rstd * g.w + b.w;
-        if (y_is_f32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + orow * ldy + c) = make_float4(o0, o1, o2, o3);
-        else *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(y) + orow * ldy + c) = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
-      }
-    }
-  }
-}
-
-// Backward, streaming.  Per row the ring slot holds [x fp32 | dy bf16 or f32 | dx_add fp32 (optional)].
-template <int NV>
-__global__ void __launch_bounds__(LNS_WARPS * 32, 1) ln_bwd_stream_kernel(
-    const void* __restrict__ dy, int dy_is_f32, long long lddy, int rpg, int gstride, int goff,
-    const float* __restrict__ x, long long ldx, const float* __restrict__ gamma, const float* __restrict__ mean,
-    const float* __restrict__ rstd, int rows, int D, float* __restrict__ dx, long long lddx,
-    const float* __restrict__ dx_add, long long ldadd, float* __restrict__ part, int want_param_grads) {
-  extern __shared__ __align__(128) uint8_t lns_smem[];
-  constexpr int NS = 2;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t xb = (uint32_t)D * 4u, dyb = (uint32_t)D * (dy_is_f32 ? 4u : 2u), ab = dx_add ? (uint32_t)D * 4u : 0u;
-  const uint32_t slot = xb + dyb + ab;
-  float* s_gamma = reinterpret_cast<float*>(lns_smem);                                    // [D], shared by the CTA
-  uint8_t* ring = lns_smem + xb + (size_t)warp * NS * slot;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(lns_smem + xb + (size_t)LNS_WARPS * NS * slot) + warp * NS;
-  for (int c = threadIdx.x * 4; c < D; c += LNS_WARPS * 32 * 4)
-    *reinterpret_cast<float4*>(s_gamma + c) = __ldg(reinterpret_cast<const float4*>(gamma + c));
-  const int gw = blockIdx.x * LNS_WARPS + warp, tw = gridDim.x * LNS_WARPS;
-  auto issue = [&](int s, long long r) {
-    uint8_t* dst = ring + (size_t)s * slot;
-    mbar_arrive_expect_tx(&bars[s], slot);
-    bulk_load_1d(dst, x + r * ldx, xb, &bars[s]);
-    const long long yr = map_row((int)r, rpg, gstride, goff);
-    bulk_load_1d(dst + xb, reinterpret_cast<const uint8_t*>(dy) + yr * lddy * (dy_is_f32 ? 4 : 2), dyb, &bars[s]);
-    if (ab) bulk_load_1d(dst + xb + dyb, dx_add + r * ldadd, ab, &bars[s]);
-  };
-  if (lane == 0) {
-    for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
-    fence_barrier_init();
-    for (int s = 0; s < NS; ++s) {
-      const long long r = (long long)gw + (long long)s * tw;
-      if (r < rows) issue(s, r);
-    }
-  }
-  __syncthreads();   // gamma staged, barriers initialised
-  float4 dg[NV], db[NV];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) { dg[i] = make_float4(0.f, 0.f, 0.f, 0.f); db[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
-  const float invD = 1.0f / (float)D;
-  int it = 0;
-  for (long long row = gw; row < rows; row += tw, ++it) {
-    const int s = it % NS;
-    mbar_wait(&bars[s], (uint32_t)((it / NS) & 1));
-    const uint8_t* base = ring + (size_t)s * slot;
-    const float4* sx = reinterpret_cast<const float4*>(base);
-    const float mu = mean[row], rs = rstd[row];
-    auto load_dy = [&](int c4) -> float4 {
-      if (dy_is_f32) return reinterpret_cast<const float4*>(base + xb)[c4];
-      const uint2 u = reinterpret_cast<const uint2*>(base + xb)[c4];
-      return make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
-    };
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c4 = i * 32 + lane;
-      if (c4 * 4 < D) {
-        const float4 xv = sx[c4], d = load_dy(c4), g = reinterpret_cast<const float4*>(s_gamma)[c4];
-        const float a0 = d.x * g.x, a1 = d.y * g.y, a2 = d.z * g.z, a3 = d.w * g.w;
-        s1 += (a0 + a1) + (a2 + a3);
-        s2 += (a0 * (xv.x - mu) + a1 * (xv.y - mu)) * rs + (a2 * (xv.z - mu) + a3 * (xv.w - mu)) * rs;
-      }
-    }
-    const float m1 = warp_sum(s1) * invD, m2 = warp_sum(s2) * invD;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c4 = i * 32 + lane;
-      if (c4 * 4 < D) {
-        const float4 xv = sx[c4], d = load_dy(c4), g = reinterpret_cast<const float4*>(s_gamma)[c4];
-        const float h0 = (xv.x - mu) * rs, h1 = (xv.y - mu) * rs, h2 = (xv.z - mu) * rs, h3 = (xv.w - mu) * rs;
-        if (dx) {
-          float4 o;
-          o.x = rs * (d.x * g.x - m1 - h0 * m2); o.y = rs * (d.y * g.y - m1 - h1 * m2);
-          o.z = rs * (d.z * g.z - m1 - h2 * m2); o.w = rs * (d.w * g.w - m1 - h3 * m2);
-          if (ab) {
-            const float4 a = reinterpret_cast<const float4*>(base + xb + dyb)[c4];
-            o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
-          }
-          *reinterpret_cast<float4*>(dx + row * lddx + c4 * 4) = o;
-        }
-        dg[i].x += d.x * h0; dg[i].y += d.y * h1; dg[i].z += d.z * h2; dg[i].w += d.w * h3;
-        db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
-      }
-    }
-    __syncwarp();   // all lanes are done with the slot
-    if (lane == 0) {
-      const long long rn = row + (long long)NS * tw;
-      if (rn < rows) issue(s, rn);
-    }
-  }
-  if (want_param_grads) {
-    float* pg = part + (long long)gw * 2 * D;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = (i * 32 + lane) * 4;
-      if (c < D) {
-        *reinterpret_cast<float4*>(pg + c) = dg[i];
-        *reinterpret_cast<float4*>(pg + D + c) = db[i];
-      }
-    }
-  }
-}
-
-static int g_ln_sms = 0;
-static int ln_num_sms() {
-  if (g_ln_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_ln_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_ln_sms <= 0) g_ln_sms = 148;
-  }
-  return g_ln_sms;
-}
-static int ln_stream_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("OFK_LN_STREAM"); v = e ? atoi(e) : 1; }
-  return v;
-}
-
 }  // namespace ofk
 
 extern "C" int ofk_layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float eps,
@@ -393,25 +192,6 @@ extern "C" int ofk_layernorm_fwd(const float* x, long long ldx, const float* gam
   if (D <= 0 || D % 4 != 0 || D > 4096) return ofk_set_error(OFK_ERR_ARG, "layernorm: D must be a multiple of 4, <= 4096");
   if (ldx % 4 != 0 || ldy % 4 != 0) return ofk_set_error(OFK_ERR_ALIGN, "layernorm: row strides must be multiples of 4");
   cudaStream_t s = (cudaStream_t)stream_;
-  if (ln_stream_enabled() && D % 128 == 0 && rows >= 2048 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
-    const int NS = D <= 2048 ? 3 : 2;
-    const size_t smem = (size_t)LNS_WARPS * NS * D * 4 + LNS_WARPS * NS * 8 + 128;
-    const int per_sm = smem <= 110 * 1024 ? 2 : 1;
-    int grid = ln_num_sms() * per_sm;
-    if (grid * LNS_WARPS > rows) grid = (rows + LNS_WARPS - 1) / LNS_WARPS;
-    static bool attr[3] = {false, false, false};
-#define OFK_LN_FWD_STREAM(NVV, IDX)                                                                                   \
-    do {                                                                                                             \
-      if (!attr[IDX]) { cudaFuncSetAttribute(ln_fwd_stream_kernel<NVV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448); attr[IDX] = true; } \
-      ln_fwd_stream_kernel<NVV><<<grid, LNS_WARPS * 32, smem, s>>>(x, ldx, gamma, beta, eps, rows, D, y, y_is_f32, ldy, rows_per_group, group_stride, group_offset, mean, rstd, NS); \
-    } while (0)
-    if (D <= 1024) OFK_LN_FWD_STREAM(8, 0);
-    else if (D <= 2048) OFK_LN_FWD_STREAM(16, 1);
-    else OFK_LN_FWD_STREAM(32, 2);
-#undef OFK_LN_FWD_STREAM
-    OFK_CHECK_LAUNCH();
-    return 0;
-  }
   const int grid = (rows + 3) / 4;
   if (D <= 1024)
     ln_fwd_kernel<8><<<grid, 128, 0, s>>>(x, ldx, gamma, beta, eps, rows, D, y, y_is_f32, ldy, rows_per_group, group_stride, group_offset, mean, rstd);
@@ -440,31 +220,8 @@ extern "C" int ofk_layernorm_bwd(const void* dy, int dy_is_f32, long long lddy, 
   if (ldx % 4 != 0 || lddy % 4 != 0 || lddx % 4 != 0 || (dx_add && ldadd % 4 != 0))
     return ofk_set_error(OFK_ERR_ALIGN, "layernorm bwd: row strides must be multiples of 4");
   cudaStream_t s = (cudaStream_t)stream_;
-  float* part = reinterpret_cast<float*>(workspace);
-  if (ln_stream_enabled() && D % 128 == 0 && D <= 2048 && rows >= 2048 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
-      (reinterpret_cast<uintptr_t>(dy) & 15) == 0 && (lddy * (dy_is_f32 ? 4 : 2)) % 16 == 0 &&
-      (!dx_add || ((reinterpret_cast<uintptr_t>(dx_add) & 15) == 0))) {
-    const size_t slot = (size_t)D * 4 + (size_t)D * (dy_is_f32 ? 4 : 2) + (dx_add ? (size_t)D * 4 : 0);
-    const size_t smem = (size_t)D * 4 + (size_t)LNS_WARPS * 2 * slot + LNS_WARPS * 2 * 8 + 128;
-    int grid = ln_num_sms();                       // one CTA (4 streaming warps) per SM; 4 * grid <= LNB_MAX_BLOCKS partials
-    if (grid * LNS_WARPS > LNB_MAX_BLOCKS) grid = LNB_MAX_BLOCKS / LNS_WARPS;
-    const int want = (dgamma || dbeta) ? 1 : 0;
-    static bool attr[2] = {false, false};
-    if (D <= 1024) {
-      if (!attr[0]) { cudaFuncSetAttribute(ln_bwd_stream_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448); attr[0] = true; }
-      ln_bwd_stream_kernel<8><<<grid, LNS_WARPS * 32, smem, s>>>(dy, dy_is_f32, lddy, rows_per_group, group_stride, group_offset, x, ldx, gamma, mean, rstd, rows, D, dx, lddx, dx_add, ldadd, part, want);
-    } else {
-      if (!attr[1]) { cudaFuncSetAttribute(ln_bwd_stream_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448); attr[1] = true; }
-      ln_bwd_stream_kernel<16><<<grid, LNS_WARPS * 32, smem, s>>>(dy, dy_is_f32, lddy, rows_per_group, group_stride, group_offset, x, ldx, gamma, mean, rstd, rows, D, dx, lddx, dx_add, ldadd, part, want);
-    }
-    OFK_CHECK_LAUNCH();
-    if (want) {
-      ln_bwd_reduce_kernel<<<(2 * D + 63) / 64, 256, 0, s>>>(part, grid * LNS_WARPS, D, dgamma, dbeta);
-      OFK_CHECK_LAUNCH();
-    }
-    return 0;
-  }
   const int nblocks = rows < LNB_MAX_BLOCKS ? rows : LNB_MAX_BLOCKS;
+  float* part = reinterpret_cast<float*>(workspace);
   if (D <= 1024)
     ln_bwd_kernel<1><<<nblocks, LNB_THREADS, 0, s>>>(dy, dy_is_f32, lddy, rows_per_group, group_stride, group_offset, x, ldx, gamma, mean, rstd, rows, D, dx, lddx, dx_add, ldadd, part);
   else if (D <= 2048)
