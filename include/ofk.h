@@ -68,6 +68,17 @@ int ofk_gemm_bf16(int epi, int a_mn_major, int b_mn_major, const void* A, long l
                   void* out2, long long ldo2, const void* aux, long long ldaux, const float* bias,
                   const float* gate, void* stream);
 
+/* Same GEMM with grouped row maps (logical row r -> (r / rows_per_group) * group_stride + group_offset + r % rpg):
+ *   out_*  : where the rows of `out` go inside a larger interleaved buffer (STORE_BF16 / BIAS_BF16 / STORE_F32);
+ *   a_k_*  : which physical rows of an MN-major A form the reduction dimension (rows_per_group % 64 == 0).
+ * Lets PerceiverAttention's k/v for the media tokens and for the latents (helpers.py:53-54: to_kv(cat(x, latents)))
+ * be produced by two GEMMs that write straight into the concatenated [b*T, v+n, 2*inner] layout, and lets the
+ * wgrads reduce over only the media (or only the latent) rows of the concatenated gradient.  0 = identity. */
+int ofk_gemm_bf16_grouped(int epi, int a_mn_major, int b_mn_major, const void* A, long long lda, const void* B,
+                          long long ldb, int M, int N, int K, int splits, int block_n, void* out, long long ldo,
+                          const float* bias, int out_rows_per_group, int out_group_stride, int out_group_offset,
+                          int a_k_rows_per_group, int a_k_group_stride, int a_k_group_offset, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm over the last dim (eps inside sqrt, affine), fp32 statistics.  nn.LayerNorm at
  * helpers.py:17,32-33,47-48,105,132,151,184.

@@ -39,6 +39,9 @@ _SIGNATURES = {
     "ofk_gemm_bf16": (c_int, [c_int, c_int, c_int, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int,
                               c_int, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p,
                               c_void_p]),
+    "ofk_gemm_bf16_grouped": (c_int, [c_int, c_int, c_int, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int,
+                                      c_int, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                      c_void_p]),
     "ofk_layernorm_fwd": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p,
                                   c_int, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "ofk_layernorm_bwd_workspace": (c_ll, [c_int, c_int]),

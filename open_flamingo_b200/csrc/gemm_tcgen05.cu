@@ -53,7 +53,15 @@ struct GemmParams {
   const float* bias;
   const float* gate;
   int stream_out;    // 1: epilogue outputs use st.global.cs (evict-first) so they do not displace the operand panels in L2
+  // Grouped row maps (0 = identity): logical row r -> (r / rpg) * gs + go + r % rpg.  `out_*` places the rows of `out`
+  // inside a larger interleaved buffer (the media / latent halves of PerceiverAttention's cat((x, latents), -2),
+  // helpers.py:53); `ak_*` does the same for the REDUCTION rows of an MN-major A operand (wgrad over one half).
+  int out_rpg, out_gs, out_go;
+  int ak_rpg, ak_gs, ak_go;
 };
+__device__ __forceinline__ long long map_rows(long long r, int rpg, int gs, int go) {
+  return rpg > 0 ? (r / rpg) * gs + go + r % rpg : r;
+}
 
 // Work item -> (m tile, n tile, k split).  Within a split, tiles are walked in groups of GROUP_M m-tiles by all
 // n-tiles, m fastest, so the ~74-148 tiles in flight share GROUP_M row panels of A and ~10-18 column panels of B
@@ -110,7 +118,8 @@ __device__ __forceinline__ void st_global_cs_v4(void* g, uint4 v) {
 
 template <int ELEM_BYTES, int MODE>
 __device__ __forceinline__ void warp_store_tile(uint32_t stage, const uint32_t* w, void* gbase, long long ld, int row0,
-                                                int col0, int M, int N, int streaming = 0) {
+                                                int col0, int M, int N, int streaming = 0, int rpg = 0, int gs = 0,
+                                                int go = 0) {
   constexpr int PIECES = ELEM_BYTES * 2;            // 16-byte pieces per 32-element row: 8 (f32) or 4 (bf16)
   constexpr int EPP = 16 / ELEM_BYTES;              // elements per piece
   const int lane = threadIdx.x & 31;
@@ -126,7 +135,7 @@ __device__ __forceinline__ void warp_store_tile(uint32_t stage, const uint32_t* 
     const uint4 v = ld_shared_v4(stage + stage_off(r, piece));
     const int row = row0 + r;
     if (row < M && col < N) {
-      uint8_t* g = reinterpret_cast<uint8_t*>(gbase) + ((long long)row * ld + col) * ELEM_BYTES;
+      uint8_t* g = reinterpret_cast<uint8_t*>(gbase) + (map_rows(row, rpg, gs, go) * ld + col) * ELEM_BYTES;
       if constexpr (MODE == 0) {
         if (streaming) st_global_cs_v4(g, v);
         else *reinterpret_cast<uint4*>(g) = v;
@@ -215,9 +224,9 @@ __device__ __forceinline__ void epilogue32(const GemmParams& p, float gate_t, ui
     }
     uint32_t w[16];
     pack32_bf16(v, w);
-    warp_store_tile<2, 0>(stage, w, p.out, p.ldo, row0, col0, p.M, p.N, p.stream_out);
+    warp_store_tile<2, 0>(stage, w, p.out, p.ldo, row0, col0, p.M, p.N, p.stream_out, p.out_rpg, p.out_gs, p.out_go);
   } else if constexpr (EPI == OFK_EPI_STORE_F32) {
-    warp_store_tile<4, 0>(stage, acc, p.out, p.ldo, row0, col0, p.M, p.N, p.stream_out);
+    warp_store_tile<4, 0>(stage, acc, p.out, p.ldo, row0, col0, p.M, p.N, p.stream_out, p.out_rpg, p.out_gs, p.out_go);
   } else if constexpr (EPI == OFK_EPI_ATOMIC_F32) {
     warp_store_tile<4, 1>(stage, acc, p.out, p.ldo, row0, col0, p.M, p.N);
   } else if constexpr (EPI == OFK_EPI_GELU_DUAL) {
@@ -254,7 +263,7 @@ __device__ __forceinline__ void epilogue32(const GemmParams& p, float gate_t, ui
       v[2 * i + 1] = bf16_round(v[2 * i + 1]) * gelu_exact_grad(bf16_hi(z[i]));
     }
     pack32_bf16(v, w);
-    warp_store_tile<2, 0>(stage, w, p.out, p.ldo, row0, col0, p.M, p.N, p.stream_out);
+    warp_store_tile<2, 0>(stage, w, p.out, p.ldo, row0, col0, p.M, p.N, p.stream_out, p.out_rpg, p.out_gs, p.out_go);
   }
 }
 
@@ -322,7 +331,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           } else {
 #pragma unroll
             for (int i = 0; i < BM / 64; ++i)                               // boxes {64 mn, 64 k}
-              tma_load_2d(sa + i * (BK * 128), &tma_a, &full_bar[stage], m0 + 64 * i, k0);
+              tma_load_2d(sa + i * (BK * 128), &tma_a, &full_bar[stage], m0 + 64 * i, (int)map_rows(k0, p.ak_rpg, p.ak_gs, p.ak_go));
           }
           if constexpr (B_MN == 0) {
             tma_load_2d(sb, &tma_b, &full_bar[stage], k0, n0);             // box {64 k, BN rows}
@@ -514,7 +523,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
             tma_load_2d_2cta(sa, &tma_a, &full_bar[stage], k0, m0);
           } else {
 #pragma unroll
-            for (int i = 0; i < 2; ++i) tma_load_2d_2cta(sa + i * (BK * 128), &tma_a, &full_bar[stage], m0 + 64 * i, k0);
+            for (int i = 0; i < 2; ++i)
+              tma_load_2d_2cta(sa + i * (BK * 128), &tma_a, &full_bar[stage], m0 + 64 * i, (int)map_rows(k0, p.ak_rpg, p.ak_gs, p.ak_go));
           }
           if constexpr (B_MN == 0) {
             tma_load_2d_2cta(sb, &tma_b, &full_bar[stage], k0, n0);
@@ -786,11 +796,16 @@ static int dispatch_epi(int epi, int a_mn, int b_mn, const CUtensorMap& ta, cons
 
 }  // namespace ofk
 
-extern "C" int ofk_gemm_bf16(int epi, int a_mn_major, int b_mn_major, const void* A, long long lda, const void* B,
-                             long long ldb, int M, int N, int K, int splits, int block_n, void* out, long long ldo,
-                             void* out2, long long ldo2, const void* aux, long long ldaux, const float* bias,
-                             const float* gate, void* stream_) {
+static int gemm_impl(int epi, int a_mn_major, int b_mn_major, const void* A, long long lda, const void* B,
+                     long long ldb, int M, int N, int K, int splits, int block_n, void* out, long long ldo,
+                     void* out2, long long ldo2, const void* aux, long long ldaux, const float* bias,
+                     const float* gate, void* stream_, int out_rpg, int out_gs, int out_go, int ak_rpg, int ak_gs,
+                     int ak_go) {
   using namespace ofk;
+  if (out_rpg > 0 && (epi != OFK_EPI_STORE_BF16 && epi != OFK_EPI_BIAS_BF16 && epi != OFK_EPI_STORE_F32))
+    return ofk_set_error(OFK_ERR_ARG, "grouped output rows are supported by the STORE_BF16 / BIAS_BF16 / STORE_F32 epilogues");
+  if (ak_rpg > 0 && (!a_mn_major || ak_rpg % 64 != 0 || K % ak_rpg != 0))
+    return ofk_set_error(OFK_ERR_ARG, "grouped reduction rows need an MN-major A with rows_per_group % 64 == 0 dividing K");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (M <= 0 || N <= 0 || K <= 0) return ofk_set_error(OFK_ERR_ARG, "GEMM dims must be positive");
   if (N % 16 != 0) return ofk_set_error(OFK_ERR_ARG, "GEMM N must be a multiple of 16");
@@ -819,6 +834,8 @@ extern "C" int ofk_gemm_bf16(int epi, int a_mn_major, int b_mn_major, const void
   p.kb_per_split = (total_kb + splits - 1) / splits;
   p.splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
   p.out = out; p.ldo = ldo; p.out2 = out2; p.ldo2 = ldo2; p.aux = aux; p.ldaux = ldaux; p.bias = bias; p.gate = gate;
+  p.out_rpg = out_rpg; p.out_gs = out_gs; p.out_go = out_go; p.ak_rpg = ak_rpg; p.ak_gs = ak_gs; p.ak_go = ak_go;
+  const int a_rows = ak_rpg > 0 ? (K / ak_rpg) * ak_gs : K;   // physical row count of an MN-major A
   {
     static int stream_mode = -1;   // OFK_GEMM_STREAM_OUT=0/1 overrides; default: stream when the outputs exceed ~32 MB
     if (stream_mode < 0) { const char* e = getenv("OFK_GEMM_STREAM_OUT"); stream_mode = e ? atoi(e) + 2 : 0; }
@@ -829,17 +846,35 @@ extern "C" int ofk_gemm_bf16(int epi, int a_mn_major, int b_mn_major, const void
   CUtensorMap ta, tb;
   int rc;
   if (two_cta) {
-    rc = a_mn_major ? get_tensor_map(A, lda, K, M, 64, BK, &ta) : get_tensor_map(A, lda, M, K, BK, 128, &ta);
+    rc = a_mn_major ? get_tensor_map(A, lda, a_rows, M, 64, BK, &ta) : get_tensor_map(A, lda, M, K, BK, 128, &ta);
     if (rc) return rc;
     rc = b_mn_major ? get_tensor_map(B, ldb, K, N, 64, BK, &tb) : get_tensor_map(B, ldb, N, K, BK, 128, &tb);
     if (rc) return rc;
     return dispatch_epi2(epi, a_mn_major, b_mn_major, ta, tb, p, stream);
   }
   // K-major: tensor [rows, K], box {64 (k), tile rows}. MN-major: tensor [K, rows], box {64 (rows), 64 (k)}.
-  rc = a_mn_major ? get_tensor_map(A, lda, K, M, 64, BK, &ta) : get_tensor_map(A, lda, M, K, BK, BM, &ta);
+  rc = a_mn_major ? get_tensor_map(A, lda, a_rows, M, 64, BK, &ta) : get_tensor_map(A, lda, M, K, BK, BM, &ta);
   if (rc) return rc;
   rc = b_mn_major ? get_tensor_map(B, ldb, K, N, 64, BK, &tb) : get_tensor_map(B, ldb, N, K, BK, BN, &tb);
   if (rc) return rc;
   if (BN == 256) return dispatch_epi<256>(epi, a_mn_major, b_mn_major, ta, tb, p, stream);
   return dispatch_epi<128>(epi, a_mn_major, b_mn_major, ta, tb, p, stream);
+}
+
+extern "C" int ofk_gemm_bf16(int epi, int a_mn_major, int b_mn_major, const void* A, long long lda, const void* B,
+                             long long ldb, int M, int N, int K, int splits, int block_n, void* out, long long ldo,
+                             void* out2, long long ldo2, const void* aux, long long ldaux, const float* bias,
+                             const float* gate, void* stream_) {
+  return gemm_impl(epi, a_mn_major, b_mn_major, A, lda, B, ldb, M, N, K, splits, block_n, out, ldo, out2, ldo2, aux, ldaux,
+                   bias, gate, stream_, 0, 0, 0, 0, 0, 0);
+}
+
+extern "C" int ofk_gemm_bf16_grouped(int epi, int a_mn_major, int b_mn_major, const void* A, long long lda, const void* B,
+                                     long long ldb, int M, int N, int K, int splits, int block_n, void* out,
+                                     long long ldo, const float* bias, int out_rows_per_group, int out_group_stride,
+                                     int out_group_offset, int a_k_rows_per_group, int a_k_group_stride,
+                                     int a_k_group_offset, void* stream_) {
+  return gemm_impl(epi, a_mn_major, b_mn_major, A, lda, B, ldb, M, N, K, splits, block_n, out, ldo, nullptr, 0, nullptr, 0,
+                   bias, nullptr, stream_, out_rows_per_group, out_group_stride, out_group_offset, a_k_rows_per_group,
+                   a_k_group_stride, a_k_group_offset);
 }

@@ -360,3 +360,109 @@ def causal_lm_loss(logits, labels, vocab_size=None, num_items_in_batch=None, ign
         return ForCausalLMLoss(logits, labels, vocab_size, num_items_in_batch=num_items_in_batch,
                                ignore_index=ignore_index, shift_labels=shift_labels, **kwargs)
     return CausalLMLossFn.apply(logits, labels.to(logits.device), ignore_index)
+
+
+# ------------------------------------------------------------------------------------------ perceiver layer, folded
+AUG = 16  # extra columns appended to the normalised media tokens: [1, 0, ..., 0] (column sums through the wgrad GEMM)
+
+
+def normalise_media(x2d, eps=1e-5):
+    """x_hat = (x - mean) / std as bf16 [rows, D + AUG] with column D == 1: computed ONCE per resampler forward --
+    the media tokens are the same for all six layers (helpers.py:129-131 only updates the latents)."""
+    rows, D = x2d.shape
+    xa = torch.empty((rows, D + AUG), device=x2d.device, dtype=bf16)
+    ones = torch.ones(D, device=x2d.device, dtype=f32)
+    zeros = torch.zeros(D, device=x2d.device, dtype=f32)
+    ops.layernorm_fwd(x2d, ones, zeros, eps, out=xa, want_stats=False)
+    xa[:, D:] = 0
+    xa[:, D] = 1
+    return xa
+
+
+class PerceiverFoldedLayerFn(torch.autograd.Function):
+    """Same math as PerceiverLayerFn with norm_media folded into to_kv:
+         to_kv(LN_media(x)) = x_hat (W_kv * gamma)^T + W_kv beta
+    so a layer touches the media tokens with exactly one GEMM forward (no LayerNorm pass, no concat copy) and one
+    wgrad GEMM backward (no media-row dgrad: x carries no gradient, flamingo.py:194), and the affine gradients
+    are recovered from the [2*inner, D] wgrad:  dW_kv += dW_eff * gamma,  dgamma = sum_c dW_eff * W_kv,
+    dbeta = W_kv^T colsum(dkv_media) (the column sums ride along as the extra ones-column of x_hat).
+    Requires v % 64 == 0 (reduction k-blocks must not straddle images)."""
+
+    @staticmethod
+    def forward(ctx, xa, latents, heads, v, nm_w, nm_b, nl_w, nl_b, wq, wkv, wout, ff_ln_w, ff_ln_b, ff_w1, ff_w2):
+        U, n, Dv = latents.shape
+        inner = wq.shape[0]
+        lat2d = latents.reshape(U * n, Dv)
+        if not lat2d.is_contiguous():
+            lat2d = lat2d.contiguous()
+        latn, l_mean, l_rstd = ops.layernorm_fwd(lat2d, nl_w, nl_b)
+        q = ops.gemm(latn, w16(wq))
+        w_eff = (wkv.detach() * nm_w.detach().unsqueeze(0)).to(bf16)             # [2*inner, Dv]
+        b_eff = torch.mv(wkv.detach(), nm_b.detach())                            # [2*inner] f32
+        kv = torch.empty((U * (v + n), 2 * inner), device=latents.device, dtype=bf16)
+        ops.gemm_grouped(xa[:, :Dv], w_eff, epi=L.EPI_BIAS_BF16, bias=b_eff, out=kv, M=U * v, N=2 * inner, K=Dv,
+                         out_map=(v, v + n, 0))
+        ops.gemm_grouped(latn, w16(wkv), epi=L.EPI_STORE_BF16, out=kv, M=U * n, N=2 * inner, K=Dv,
+                         out_map=(n, v + n, v))
+        kv3 = kv.view(U, v + n, 2 * inner)
+        o, lse = ops.attn_fwd(q.view(U, n, inner), kv3[..., :inner], kv3[..., inner:], heads,
+                              float((inner // heads) ** -0.5))
+        lat1 = ops.gemm(o.view(U * n, inner), w16(wout), epi=L.EPI_GATE_RESID_F32, aux=lat2d)
+        out, ff_saved = _ffn_forward(lat1, ff_ln_w, ff_ln_b, ff_w1, ff_w2, None)
+        ctx.save_for_backward(xa, lat2d, latn, l_mean, l_rstd, q, kv, o, lse, lat1, *ff_saved[:5], nm_w, nl_w, wq, wkv,
+                              wout, ff_ln_w, ff_w1, ff_w2)
+        ctx.meta = (U, v, n, Dv, inner, heads)
+        ctx.params = (nm_w, nm_b, nl_w, nl_b, wq, wkv, wout, ff_ln_w, ff_ln_b, ff_w1, ff_w2)
+        return out.view(U, n, Dv)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (xa, lat2d, latn, l_mean, l_rstd, q, kv, o, lse, lat1, f_xn, f_mean, f_rstd, f_z, f_h, nm_w, nl_w, wq, wkv, wout,
+         ff_ln_w, ff_w1, ff_w2) = ctx.saved_tensors
+        U, v, n, Dv, inner, heads = ctx.meta
+        needs = ctx.needs_input_grad
+        names = ("nm_w", "nm_b", "nl_w", "nl_b", "wq", "wkv", "wout", "ff_ln_w", "ff_ln_b", "ff_w1", "ff_w2")
+        sinks = {nm: _GradSink(p, needs[4 + i]) for i, (nm, p) in enumerate(zip(names, ctx.params))}
+        sinks["gate"] = _GradSink(None, False)
+        dout2d = dout.reshape(U * n, Dv)
+        if not dout2d.is_contiguous():
+            dout2d = dout2d.contiguous()
+        if dout2d.dtype != f32:
+            dout2d = dout2d.float()
+        dlat1 = _ffn_backward(dout2d, lat1, (f_xn, f_mean, f_rstd, f_z, f_h, None), ff_ln_w, ff_w1, ff_w2, None,
+                              {"ln_w": sinks["ff_ln_w"], "ln_b": sinks["ff_ln_b"], "w1": sinks["ff_w1"],
+                               "w2": sinks["ff_w2"], "gate": sinks["gate"]})
+        da = ops.gate_bwd(dlat1, None, None, None)
+        _wgrad(da, o.view(U * n, inner), sinks["wout"])
+        d_o = ops.gemm(da, w16(wout), b_mn=True)
+        del da
+        kv3 = kv.view(U, v + n, 2 * inner)
+        dkv = torch.empty_like(kv)
+        dkv3 = dkv.view(U, v + n, 2 * inner)
+        dq, _, _ = ops.attn_bwd(q.view(U, n, inner), kv3[..., :inner], kv3[..., inner:], o, d_o.view(U, n, inner), lse,
+                                heads, float((inner // heads) ** -0.5), dk=dkv3[..., :inner], dv=dkv3[..., inner:])
+        dq2 = dq.view(U * n, inner)
+        _wgrad(dq2, latn, sinks["wq"])
+        # latent rows: ordinary wgrad / dgrad on a compact copy (U*n rows -- small)
+        dkv_lat = dkv3[:, v:, :].reshape(U * n, 2 * inner)
+        _wgrad(dkv_lat, latn, sinks["wkv"])
+        # media rows: ONE wgrad over only the media rows of the concatenated gradient, against [x_hat | 1]
+        if sinks["wkv"].needs or sinks["nm_w"].needs or sinks["nm_b"].needs:
+            dweff = torch.zeros((2 * inner, Dv + AUG), device=kv.device, dtype=f32)
+            ops.gemm_grouped(dkv, xa, a_mn=True, b_mn=True, epi=L.EPI_ATOMIC_F32, out=dweff, M=2 * inner, N=Dv + AUG,
+                             K=U * v, splits=_wgrad_splits(2 * inner, Dv + AUG, U * v), ak_map=(v, v + n, 0))
+            dw = dweff[:, :Dv]
+            if sinks["wkv"].needs:
+                sinks["wkv"].buffer().addcmul_(dw, nm_w.detach().unsqueeze(0))
+            if sinks["nm_w"].needs:
+                sinks["nm_w"].buffer().add_((dw * wkv.detach()).sum(0))
+            if sinks["nm_b"].needs:
+                sinks["nm_b"].buffer().add_(torch.mv(wkv.detach().t(), dweff[:, Dv]))
+        dlatn_q = ops.gemm(dq2, w16(wq), b_mn=True)
+        dlat = ops.layernorm_bwd(dlatn_q, lat2d, nl_w, l_mean, l_rstd, dgamma=sinks["nl_w"].buffer(),
+                                 dbeta=sinks["nl_b"].buffer(), dx_add=dlat1)
+        dlatn_kv = ops.gemm(dkv_lat, w16(wkv), b_mn=True)
+        dlat = ops.layernorm_bwd(dlatn_kv, lat2d, nl_w, l_mean, l_rstd, dgamma=sinks["nl_w"].buffer(),
+                                 dbeta=sinks["nl_b"].buffer(), dx=dlat, dx_add=dlat)
+        grads = [sinks[nm].result() for nm in names]
+        return (None, dlat.view(U, n, Dv) if needs[1] else None, None, None, *grads)

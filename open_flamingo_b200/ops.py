@@ -294,3 +294,20 @@ def attn_dense_bwd(q, k, v, o, d_o, lse, heads, head_dim, scale, *, causal=False
                                        lddk, dvb, lddv, scale, int(causal), L.ptr(mask), L.ptr(slopes),
                                        L.ptr(pure_causal_flag), L.stream_ptr()))
     return dq, dk, dv
+
+
+def gemm_grouped(a, b, *, a_mn=False, b_mn=False, epi=L.EPI_STORE_BF16, out, M, N, K, bias=None, splits=1, block_n=0,
+                 out_map=(0, 0, 0), ak_map=(0, 0, 0)):
+    """GEMM with grouped row maps (see ofk_gemm_bf16_grouped): `out_map` = (rows_per_group, group_stride,
+    group_offset) for the rows of `out`; `ak_map` the same for the reduction rows of an MN-major `a`."""
+    L.require_cuda(a, b, out)
+    _rowmajor_2d(a, "a")
+    _rowmajor_2d(b, "b")
+    _rowmajor_2d(out, "out")
+    if a.dtype != bf16 or b.dtype != bf16:
+        raise ValueError("gemm operands must be bfloat16")
+    L.check(L.lib().ofk_gemm_bf16_grouped(
+        epi, int(a_mn), int(b_mn), a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), M, N, K, splits, block_n,
+        out.data_ptr(), out.stride(0), L.ptr(bias), out_map[0], out_map[1], out_map[2], ak_map[0], ak_map[1], ak_map[2],
+        L.stream_ptr()))
+    return out

@@ -92,11 +92,22 @@ class PerceiverResampler(nn.Module):
         x3 = x.reshape(U, F * v, D).contiguous()
         n = self.latents.shape[0]
         latents = self.latents.unsqueeze(0).expand(U, n, D)  # broadcast view; grads reduce back over U
-        for attn, ff in self.layers:
-            latents = fused.PerceiverLayerFn.apply(
-                x3, latents, attn.heads, attn.norm_media.weight, attn.norm_media.bias, attn.norm_latents.weight,
-                attn.norm_latents.bias, attn.to_q.weight, attn.to_kv.weight, attn.to_out.weight,
-                ff[0].weight, ff[0].bias, ff[1].weight, ff[3].weight)
+        vtok = F * v
+        if vtok % 64 == 0 and D % 64 == 0:
+            # the media tokens never change across layers: normalise them once and fold each layer's norm_media
+            # affine into its to_kv weights (fused.PerceiverFoldedLayerFn)
+            xa = fused.normalise_media(x3.view(U * vtok, D), self.layers[0][0].norm_media.eps)
+            for attn, ff in self.layers:
+                latents = fused.PerceiverFoldedLayerFn.apply(
+                    xa, latents, attn.heads, vtok, attn.norm_media.weight, attn.norm_media.bias,
+                    attn.norm_latents.weight, attn.norm_latents.bias, attn.to_q.weight, attn.to_kv.weight,
+                    attn.to_out.weight, ff[0].weight, ff[0].bias, ff[1].weight, ff[3].weight)
+        else:
+            for attn, ff in self.layers:
+                latents = fused.PerceiverLayerFn.apply(
+                    x3, latents, attn.heads, attn.norm_media.weight, attn.norm_media.bias, attn.norm_latents.weight,
+                    attn.norm_latents.bias, attn.to_q.weight, attn.to_kv.weight, attn.to_out.weight,
+                    ff[0].weight, ff[0].bias, ff[1].weight, ff[3].weight)
         out = fused.FinalNormFn.apply(latents, self.norm.weight, self.norm.bias)
         return out.view(b, T, n, D)
 

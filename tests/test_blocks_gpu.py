@@ -231,3 +231,29 @@ def test_perceiver_isolation_shape_vs_oracle():
     cmp(y, y_ref, OUT_TOL, "C5 perceiver y")
     for k, p in m.named_parameters():
         cmp(p.grad, g_ref[k], GRAD_TOL, f"C5 perceiver grad {k}")
+
+
+@pytest.mark.parametrize("v,dim,U", [(64, 128, 3), (192, 256, 2)])
+def test_perceiver_folded_path_vs_oracle(v, dim, U):
+    """v % 64 == 0 takes the folded path (norm_media folded into to_kv, media tokens normalised once): outputs and
+    EVERY parameter gradient -- in particular norm_media.{weight,bias} and to_kv.weight, which are reconstructed
+    from the folded wgrad -- against the fp32 oracle."""
+    from open_flamingo_b200.src.helpers import PerceiverResampler
+    from oracle import flamingo_oracle as O
+    torch.manual_seed(31)
+    m = PerceiverResampler(dim=dim, depth=2)
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            if "norm" in name:   # make the affine terms non-trivial
+                p.add_(0.2 * torch.randn_like(p))
+    sd_cpu = {k: v_.detach().clone() for k, v_ in m.state_dict().items()}
+    m = m.cuda()
+    x = torch.randn(U, 1, 1, v, dim) * 1.5 + 0.3
+    w = torch.randn(U, 1, 64, dim)
+    y = m(x.cuda())
+    (y * w.cuda()).sum().backward()
+    y_ref, g_ref, _ = oracle_grads(lambda sd, xx: (O.perceiver_resampler(xx, sd), w), sd_cpu, x)
+    cmp(y, y_ref, OUT_TOL, "folded perceiver y")
+    for k, p in m.named_parameters():
+        assert p.grad is not None, k
+        cmp(p.grad, g_ref[k], GRAD_TOL, f"folded perceiver grad {k}")
