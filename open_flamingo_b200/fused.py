@@ -384,7 +384,8 @@ class PerceiverFoldedLayerFn(torch.autograd.Function):
          to_kv(LN_media(x)) = x_hat (W_kv * gamma)^T + W_kv beta
     so a layer touches the media tokens with exactly one GEMM forward (no LayerNorm pass, no concat copy) and one
     wgrad GEMM backward (no media-row dgrad: x carries no gradient, flamingo.py:194), and the affine gradients
-    are recovered from the [2*inner, D] wgrad:  dW_kv += dW_eff * gamma,  dgamma = sum_c dW_eff * W_kv,
+    are recovered from the [2*inner, D] wgrad:  dW_kv += dW_eff * gamma + colsum(dkv_media) beta^T,
+    dgamma = sum_c dW_eff * W_kv,
     dbeta = W_kv^T colsum(dkv_media) (the column sums ride along as the extra ones-column of x_hat).
     Requires v % 64 == 0 (reduction k-blocks must not straddle images)."""
 
@@ -452,8 +453,9 @@ class PerceiverFoldedLayerFn(torch.autograd.Function):
             ops.gemm_grouped(dkv, xa, a_mn=True, b_mn=True, epi=L.EPI_ATOMIC_F32, out=dweff, M=2 * inner, N=Dv + AUG,
                              K=U * v, splits=_wgrad_splits(2 * inner, Dv + AUG, U * v), ak_map=(v, v + n, 0))
             dw = dweff[:, :Dv]
-            if sinks["wkv"].needs:
+            if sinks["wkv"].needs:   # d/dW[c, j] of sum_j W[c, j] (x_hat_j gamma_j + beta_j)
                 sinks["wkv"].buffer().addcmul_(dw, nm_w.detach().unsqueeze(0))
+                sinks["wkv"].buffer().addr_(dweff[:, Dv], ctx.params[1].detach())
             if sinks["nm_w"].needs:
                 sinks["nm_w"].buffer().add_((dw * wkv.detach()).sum(0))
             if sinks["nm_b"].needs:
