@@ -399,7 +399,8 @@ class PerceiverFoldedLayerFn(torch.autograd.Function):
         latn, l_mean, l_rstd = ops.layernorm_fwd(lat2d, nl_w, nl_b)
         q = ops.gemm(latn, w16(wq))
         w_eff = (wkv.detach() * nm_w.detach().unsqueeze(0)).to(bf16)             # [2*inner, Dv]
-        b_eff = torch.mv(wkv.detach(), nm_b.detach())                            # [2*inner] f32
+        with torch.autocast("cuda", enabled=False):   # autocast would hand back a bf16 vector; the epilogue reads f32
+            b_eff = torch.mv(wkv.detach(), nm_b.detach())                        # [2*inner] f32
         kv = torch.empty((U * (v + n), 2 * inner), device=latents.device, dtype=bf16)
         ops.gemm_grouped(xa[:, :Dv], w_eff, epi=L.EPI_BIAS_BF16, bias=b_eff, out=kv, M=U * v, N=2 * inner, K=Dv,
                          out_map=(v, v + n, 0))
@@ -459,7 +460,8 @@ class PerceiverFoldedLayerFn(torch.autograd.Function):
             if sinks["nm_w"].needs:
                 sinks["nm_w"].buffer().add_((dw * wkv.detach()).sum(0))
             if sinks["nm_b"].needs:
-                sinks["nm_b"].buffer().add_(torch.mv(wkv.detach().t(), dweff[:, Dv]))
+                with torch.autocast("cuda", enabled=False):
+                    sinks["nm_b"].buffer().add_(torch.mv(wkv.detach().t(), dweff[:, Dv]))
         dlatn_q = ops.gemm(dq2, w16(wq), b_mn=True)
         dlat = ops.layernorm_bwd(dlatn_q, lat2d, nl_w, l_mean, l_rstd, dgamma=sinks["nl_w"].buffer(),
                                  dbeta=sinks["nl_b"].buffer(), dx_add=dlat1)

@@ -48,6 +48,10 @@ def gemm(a, b, *, a_mn=False, b_mn=False, epi=L.EPI_STORE_BF16, out=None, out2=N
         _rowmajor_2d(out2, "out2")
     if aux is not None:
         _rowmajor_2d(aux, "aux")
+    if bias is not None and (bias.dtype != f32 or bias.numel() < N or not bias.is_contiguous()):
+        raise ValueError("gemm bias must be a contiguous float32 vector of length >= N")
+    if gate is not None and gate.dtype != f32:
+        raise ValueError("gemm gate must be float32")
     L.check(L.lib().ofk_gemm_bf16(
         epi, int(a_mn), int(b_mn), a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), M, N, K, splits, block_n,
         out.data_ptr(), out.stride(0), L.ptr(out2), 0 if out2 is None else out2.stride(0),
@@ -306,6 +310,8 @@ def gemm_grouped(a, b, *, a_mn=False, b_mn=False, epi=L.EPI_STORE_BF16, out, M, 
     _rowmajor_2d(out, "out")
     if a.dtype != bf16 or b.dtype != bf16:
         raise ValueError("gemm operands must be bfloat16")
+    if bias is not None and (bias.dtype != f32 or bias.numel() < N or not bias.is_contiguous()):
+        raise ValueError("gemm bias must be a contiguous float32 vector of length >= N")
     L.check(L.lib().ofk_gemm_bf16_grouped(
         epi, int(a_mn), int(b_mn), a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), M, N, K, splits, block_n,
         out.data_ptr(), out.stride(0), L.ptr(bias), out_map[0], out_map[1], out_map[2], ak_map[0], ak_map[1], ak_map[2],

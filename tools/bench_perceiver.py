@@ -12,10 +12,10 @@ import torch
 from open_flamingo_b200 import _lib
 from open_flamingo_b200.src.helpers import PerceiverResampler
 
-U, v, D, n, depth = 64, 4096, 1024, 64, 6
+U, v, D, n, depth = 64, int(os.environ.get("V", 4096)), 1024, 64, 6
 torch.manual_seed(0)
 m = PerceiverResampler(dim=D, depth=depth).cuda()
-x = torch.randn(8, 8, 1, v, D, device="cuda")
+x = torch.randn(8, 8, 1, v, D, device="cuda").to(getattr(torch, os.environ.get("XDTYPE", "float32")))
 w = torch.randn(8, 8, n, D, device="cuda")
 
 
@@ -26,12 +26,12 @@ def step():
     (y * w).sum().backward()
 
 
-for _ in range(3):
+for _ in range(int(os.environ.get("WARM", 3))):
     step()
 torch.cuda.synchronize()
 l0 = _lib.launch_count()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-iters = 5
+iters = int(os.environ.get("ITERS", 5))
 e0.record()
 for _ in range(iters):
     step()
