@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(LNB_THREADS) ln_bwd_kernel(
       }
     }
   }
+  if (part == nullptr) return;   // frozen LayerNorm (the LM's own norms): only dx is wanted
   float* pg = part + (long long)blockIdx.x * 2 * D;
 #pragma unroll
   for (int g = 0; g < G; ++g) {
@@ -163,21 +164,32 @@ __global__ void __launch_bounds__(LNB_THREADS) ln_bwd_kernel(
 }
 
 // Column-sum of the per-block partials: 64 columns x 4 row groups per 256-thread block (coalesced 256-byte row
-// segments, 4x the parallelism of one-thread-per-column), then a shared-memory fold of the row groups.
+// segments), the partial rows split over gridDim.y chunks so ~500 blocks share the 2 * D * nblocks floats (a
+// 64-block grid left more than half of the SMs idle and took as long as the backward kernel's own tail);
+// chunk results are combined with one red.global.add per column (dgamma / dbeta accumulate anyway).
+constexpr int LNR_CHUNKS = 8;
 __global__ void __launch_bounds__(256) ln_bwd_reduce_kernel(const float* __restrict__ part, int nblocks, int D,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta) {
   __shared__ float s_acc[4][64];
   const int c = blockIdx.x * 64 + (threadIdx.x & 63);  // over 2*D
   const int rg = threadIdx.x >> 6;
-  float s = 0.f;
-  if (c < 2 * D)
-    for (int b = rg; b < nblocks; b += 4) s += part[(long long)b * 2 * D + c];
-  s_acc[rg][threadIdx.x & 63] = s;
+  const int per = (nblocks + gridDim.y - 1) / gridDim.y;
+  const int b0 = blockIdx.y * per, b1 = min(nblocks, b0 + per);
+  float s0 = 0.f, s1 = 0.f;
+  if (c < 2 * D) {
+    int b = b0 + rg;
+    for (; b + 4 < b1; b += 8) {
+      s0 += part[(long long)b * 2 * D + c];
+      s1 += part[(long long)(b + 4) * 2 * D + c];
+    }
+    if (b < b1) s0 += part[(long long)b * 2 * D + c];
+  }
+  s_acc[rg][threadIdx.x & 63] = s0 + s1;
   __syncthreads();
   if (rg == 0 && c < 2 * D) {
-    s = (s_acc[0][threadIdx.x] + s_acc[1][threadIdx.x]) + (s_acc[2][threadIdx.x] + s_acc[3][threadIdx.x]);
-    if (c < D) { if (dgamma) dgamma[c] += s; }
-    else if (dbeta) dbeta[c - D] += s;
+    const float s = (s_acc[0][threadIdx.x] + s_acc[1][threadIdx.x]) + (s_acc[2][threadIdx.x] + s_acc[3][threadIdx.x]);
+    if (c < D) { if (dgamma) atomicAdd(dgamma + c, s); }
+    else if (dbeta) atomicAdd(dbeta + (c - D), s);
   }
 }
 
@@ -221,7 +233,7 @@ extern "C" int ofk_layernorm_bwd(const void* dy, int dy_is_f32, long long lddy, 
     return ofk_set_error(OFK_ERR_ALIGN, "layernorm bwd: row strides must be multiples of 4");
   cudaStream_t s = (cudaStream_t)stream_;
   const int nblocks = rows < LNB_MAX_BLOCKS ? rows : LNB_MAX_BLOCKS;
-  float* part = reinterpret_cast<float*>(workspace);
+  float* part = (dgamma || dbeta) ? reinterpret_cast<float*>(workspace) : nullptr;
   if (D <= 1024)
     ln_bwd_kernel<1><<<nblocks, LNB_THREADS, 0, s>>>(dy, dy_is_f32, lddy, rows_per_group, group_stride, group_offset, x, ldx, gamma, mean, rstd, rows, D, dx, lddx, dx_add, ldadd, part);
   else if (D <= 2048)
@@ -230,7 +242,7 @@ extern "C" int ofk_layernorm_bwd(const void* dy, int dy_is_f32, long long lddy, 
     ln_bwd_kernel<4><<<nblocks, LNB_THREADS, 0, s>>>(dy, dy_is_f32, lddy, rows_per_group, group_stride, group_offset, x, ldx, gamma, mean, rstd, rows, D, dx, lddx, dx_add, ldadd, part);
   OFK_CHECK_LAUNCH();
   if (dgamma || dbeta) {
-    ln_bwd_reduce_kernel<<<(2 * D + 63) / 64, 256, 0, s>>>(part, nblocks, D, dgamma, dbeta);
+    ln_bwd_reduce_kernel<<<dim3((2 * D + 63) / 64, nblocks >= 64 ? LNR_CHUNKS : 1), 256, 0, s>>>(part, nblocks, D, dgamma, dbeta);
     OFK_CHECK_LAUNCH();
   }
   return 0;
