@@ -36,6 +36,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gemm-shapes", default=None, help="write the per-shape GEMM table of the instrumented pass here")
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--t_img", type=int, default=2)
     ap.add_argument("--t_txt", type=int, default=256)
@@ -123,31 +124,51 @@ class GemmTimer:
         self.records = []
 
     def wrap(self, ops_mod):
-        orig = ops_mod.gemm
         timer = self
 
-        def timed_gemm(a, b, **kw):
-            e0 = torch.cuda.Event(enable_timing=True)
-            e1 = torch.cuda.Event(enable_timing=True)
-            e0.record()
-            out = orig(a, b, **kw)
-            e1.record()
-            a_mn, b_mn = kw.get("a_mn", False), kw.get("b_mn", False)
-            m, k = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
-            n = b.shape[1] if b_mn else b.shape[0]
-            timer.records.append((e0, e1, 2.0 * m * n * k, kw.get("epi", 0), int(a_mn), int(b_mn)))
-            return out
+        def make(orig):
+            def timed(a, b, **kw):
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out = orig(a, b, **kw)
+                e1.record()
+                a_mn, b_mn = kw.get("a_mn", False), kw.get("b_mn", False)
+                m, k = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
+                n = b.shape[1] if b_mn else b.shape[0]
+                m, n, k = kw.get("M") or m, kw.get("N") or n, kw.get("K") or k
+                timer.records.append((e0, e1, 2.0 * m * n * k, kw.get("epi", 0), int(a_mn), int(b_mn),
+                                      (m, n, k, kw.get("splits", 1))))
+                return out
+            return timed
 
-        self._orig, self._mod = orig, ops_mod
-        ops_mod.gemm = timed_gemm  # fused.py / vit.py call `ops.gemm` through the module, so this covers them
+        self._mod = ops_mod
+        self._orig = {name: getattr(ops_mod, name) for name in ("gemm", "gemm_grouped")}
+        for name, fn in self._orig.items():   # fused.py / vit.py call these through the module, so this covers them
+            setattr(ops_mod, name, make(fn))
 
     def unwrap(self):
-        self._mod.gemm = self._orig
+        for name, fn in self._orig.items():
+            setattr(self._mod, name, fn)
+
+    def by_shape(self, steps):
+        """Per (variant, M, N, K, splits): launches/step, mean us, TFLOP/s, tiles and waves of the 2-CTA 256x256 grid."""
+        acc = {}
+        for e0, e1, flop, epi, a_mn, b_mn, shape in self.records:
+            d = acc.setdefault((epi, a_mn, b_mn) + shape, [0.0, 0.0, 0])
+            d[0] += e0.elapsed_time(e1); d[1] += flop; d[2] += 1
+        rows = []
+        for (epi, a_mn, b_mn, m, n, k, splits), (ms, flop, cnt) in acc.items():
+            tiles = ((m + 255) // 256) * ((n + 255) // 256) * splits
+            rows.append({"epi": epi, "a_mn": a_mn, "b_mn": b_mn, "M": m, "N": n, "K": k, "splits": splits,
+                         "launches_per_step": cnt / steps, "ms_per_step": ms / steps, "us_per_launch": 1e3 * ms / cnt,
+                         "TFLOP/s": flop / (ms * 1e-3) / 1e12 if ms else 0.0, "tiles": tiles, "waves_74": tiles / 74.0})
+        return sorted(rows, key=lambda r: -r["ms_per_step"])
 
     def summary(self):
         tot_ms, tot_flop = 0.0, 0.0
         by = {}
-        for e0, e1, flop, epi, a_mn, b_mn in self.records:
+        for e0, e1, flop, epi, a_mn, b_mn, _shape in self.records:
             ms = e0.elapsed_time(e1)
             tot_ms += ms
             tot_flop += flop
@@ -355,6 +376,9 @@ def run_ours(args):
     ms_instr = timed(lambda: train_step(resident), args.steps)
     timer.unwrap()
     gemm_ms, gemm_flop, gemm_n, gemm_by = timer.summary()
+    if args.gemm_shapes and rank == 0:
+        with open(args.gemm_shapes, "w") as f:
+            json.dump(timer.by_shape(args.steps), f, indent=1)
 
     # ---- end-to-end timing: pinned host inputs -> device every step, loss read back every step
     def e2e_step():

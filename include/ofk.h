@@ -68,6 +68,20 @@ int ofk_gemm_bf16(int epi, int a_mn_major, int b_mn_major, const void* A, long l
                   void* out2, long long ldo2, const void* aux, long long ldaux, const float* bias,
                   const float* gate, void* stream);
 
+/* Same GEMM with a caller-owned scratch buffer that enables the "tail split": when the last round of the persistent
+ * 256 x 256-tile grid would be at most half full (e.g. the N = 2048 projections of MPT-1B: 256 tiles on 74 SM pairs =
+ * 3.46 rounds), its tiles are cut into 2-4 k-slices that run on the otherwise idle SM pairs; the slices exchange fp32
+ * partial accumulators through `workspace` (L2-resident) and the last slice applies the fused epilogue, so results
+ * do not depend on whether the split is taken beyond fp32 summation order.  `workspace` must hold at least
+ * ofk_gemm_workspace_bytes() bytes, be 16-byte aligned, have its first 4096 bytes zeroed once before first use, and
+ * must not be shared by GEMMs that may run concurrently (one buffer per stream).  NULL = plain ofk_gemm_bf16.
+ * Replaces the same reference lines as ofk_gemm_bf16. */
+long long ofk_gemm_workspace_bytes(void);
+int ofk_gemm_bf16_ws(int epi, int a_mn_major, int b_mn_major, const void* A, long long lda, const void* B,
+                     long long ldb, int M, int N, int K, int splits, int block_n, void* out, long long ldo,
+                     void* out2, long long ldo2, const void* aux, long long ldaux, const float* bias,
+                     const float* gate, void* workspace, long long workspace_bytes, void* stream);
+
 /* Same GEMM with grouped row maps (logical row r -> (r / rows_per_group) * group_stride + group_offset + r % rpg):
  *   out_*  : where the rows of `out` go inside a larger interleaved buffer (STORE_BF16 / BIAS_BF16 / STORE_F32);
  *   a_k_*  : which physical rows of an MN-major A form the reduction dimension (rows_per_group % 64 == 0).

@@ -58,6 +58,15 @@ struct GemmParams {
   // helpers.py:53); `ak_*` does the same for the REDUCTION rows of an MN-major A operand (wgrad over one half).
   int out_rpg, out_gs, out_go;
   int ak_rpg, ak_gs, ak_go;
+  // Tail split (2-CTA kernel, splits == 1): the tiles of the last, partially filled round of the persistent grid
+  // are cut into `tail_s` k-slices that run on otherwise idle SM pairs.  Slices 0..tail_s-2 dump their fp32
+  // accumulators into `tail_ws` (register order, coalesced) and bump a per-warp flag; the last slice waits for the
+  // flags, adds the partials to its own accumulator and runs the normal fused epilogue.  tail_s == 0: off.
+  int tail_first;    // first rasterised tile index of the tail round
+  int tail_s;        // k-slices per tail tile (2..4)
+  int tail_kps;      // k-blocks per slice
+  float* tail_ws;    // [(rem * (tail_s - 1))][2 CTAs][8 warps][4 rounds][8][32 lanes][4] floats
+  int* tail_flags;   // [rem][2 CTAs][8 warps]
 };
 __device__ __forceinline__ long long map_rows(long long r, int rpg, int gs, int go) {
   return rpg > 0 ? (r / rpg) * gs + go + r % rpg : r;
@@ -77,6 +86,42 @@ __device__ __forceinline__ void work_to_tile(int w, int m_tiles, int n_tiles, in
   const int in_g = r - g * group_sz;
   mt = first_m + in_g % gm;
   nt = in_g / gm;
+}
+
+// Work item of the 2-CTA kernel -> tile, k-block range and tail-split role (0 = whole tile, 1 = partial producer,
+// 2 = owner of a split tile).
+struct Work2 { int mt, nt, kb0, kb1, role, t, j; };
+__device__ __forceinline__ Work2 decode_work2(const GemmParams& p, int w, int m_tiles, int n_tiles, int total_kb) {
+  Work2 o;
+  int ks;
+  if (p.tail_s > 0 && w >= p.tail_first) {
+    const int u = w - p.tail_first;
+    o.t = u / p.tail_s;
+    o.j = u - o.t * p.tail_s;
+    work_to_tile(p.tail_first + o.t, m_tiles, n_tiles, o.mt, o.nt, ks);
+    o.kb0 = o.j * p.tail_kps;
+    o.kb1 = min(total_kb, o.kb0 + p.tail_kps);
+    o.role = (o.j == p.tail_s - 1) ? 2 : 1;
+  } else {
+    work_to_tile(w, m_tiles, n_tiles, o.mt, o.nt, ks);
+    o.kb0 = ks * p.kb_per_split;
+    o.kb1 = min(total_kb, o.kb0 + p.kb_per_split);
+    o.role = 0; o.t = 0; o.j = 0;
+  }
+  return o;
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_global_cg_v4(void* g, uint4 v) {
+  asm volatile("st.global.cg.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(g), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_global_cg_v4(const void* g) {
+  uint4 v;
+  asm volatile("ld.global.cg.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(g) : "memory");
+  return v;
 }
 
 template <int BN>
@@ -478,8 +523,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
 
   const int m_tiles = (p.M + 255) / 256;
   const int n_tiles = (p.N + BN2 - 1) / BN2;
-  const int num_work = m_tiles * n_tiles * p.splits;
   const int total_kb = (p.K + BK - 1) / BK;
+  const int num_work = p.tail_s > 0 ? p.tail_first + (m_tiles * n_tiles - p.tail_first) * p.tail_s
+                                    : m_tiles * n_tiles * p.splits;
   const int first_work = (int)cluster_id_x();
   const int work_stride = (int)num_clusters_x();
 
@@ -507,12 +553,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int w = first_work; w < num_work; w += work_stride) {
-        int mt, nt, ks;
-        work_to_tile(w, m_tiles, n_tiles, mt, nt, ks);
-        const int m0 = mt * 256 + (int)cta_rank * 128;
-        const int n0 = nt * BN2 + (int)cta_rank * 128;
-        const int kb0 = ks * p.kb_per_split;
-        const int kb1 = min(total_kb, kb0 + p.kb_per_split);
+        const Work2 wk = decode_work2(p, w, m_tiles, n_tiles, total_kb);
+        const int m0 = wk.mt * 256 + (int)cta_rank * 128;
+        const int n0 = wk.nt * BN2 + (int)cta_rank * 128;
+        const int kb0 = wk.kb0, kb1 = wk.kb1;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
@@ -544,9 +588,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
       for (int w = first_work; w < num_work; w += work_stride) {
-        const int ks = w / (m_tiles * n_tiles);
-        const int kb0 = ks * p.kb_per_split;
-        const int kb1 = min(total_kb, kb0 + p.kb_per_split);
+        const Work2 wk = decode_work2(p, w, m_tiles, n_tiles, total_kb);
+        const int kb0 = wk.kb0, kb1 = wk.kb1;
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN2;
@@ -581,12 +624,38 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     }
     int as = 0; uint32_t aphase = 0;
     for (int w = first_work; w < num_work; w += work_stride) {
-      int mt, nt, ks_unused;
-      work_to_tile(w, m_tiles, n_tiles, mt, nt, ks_unused);
+      const Work2 wk = decode_work2(p, w, m_tiles, n_tiles, total_kb);
+      const int mt = wk.mt, nt = wk.nt;
       const int n0 = nt * BN2;
+      const int wslot = (int)cta_rank * NUM_EPI_WARPS + warp;   // this warp's slot inside a tile's partials / flags
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN2 + half * (BN2 / 2);
+      if (wk.role == 1) {
+        // ---- tail-split producer: dump this warp's 32 x 128 fp32 accumulators in register order, then signal
+        float* wsp = p.tail_ws + ((size_t)(wk.t * (p.tail_s - 1) + wk.j) * (2 * NUM_EPI_WARPS) + wslot) * 4096 + lane * 4;
+#pragma unroll 1
+        for (int c = 0; c < BN2 / 64; ++c) {
+          uint32_t acc[32];
+          tmem_ld16(taddr + c * 32, *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));
+          tmem_ld16(taddr + c * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&acc[16]));
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            st_global_cg_v4(wsp + c * 1024 + i * 128, make_uint4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]));
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence();
+          atomicAdd(p.tail_flags + wk.t * (2 * NUM_EPI_WARPS) + wslot, 1);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&tmem_empty[as], 0);
+        if (++as == 2) { as = 0; aphase ^= 1; }
+        continue;
+      }
       const uint32_t stage_addr = smem_u32(smem + STAGES * L::STAGE_BYTES + L::BAR_BYTES) + warp * STAGE_BYTES_PER_WARP;
       const int row0 = mt * 256 + (int)cta_rank * 128 + q * 32;
       constexpr int AUXB = AuxBytes<EPI>::value;
@@ -594,6 +663,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
       const int colbase = n0 + half * (BN2 / 2);
       if constexpr (AUXB != 0) {
         if (row0 < p.M && colbase < p.N) aux_prefetch<AUXB>(pre, p.aux, p.ldaux, row0, colbase, p.M, p.N);
+      }
+      const float* wsp = nullptr;
+      if (wk.role == 2) {
+        // ---- tail-split owner: wait until the other slices' partials for this warp slot have landed
+        int* flag = p.tail_flags + wk.t * (2 * NUM_EPI_WARPS) + wslot;
+        if (lane == 0) {
+          while (ld_acquire_gpu(flag) < p.tail_s - 1) __nanosleep(64);
+          *flag = 0;                                   // single consumer: ready for the next launch
+        }
+        __syncwarp();
+        __threadfence();
+        wsp = p.tail_ws + ((size_t)(wk.t * (p.tail_s - 1)) * (2 * NUM_EPI_WARPS) + wslot) * 4096 + lane * 4;
       }
 #pragma unroll 1
       for (int c = 0; c < BN2 / 64; ++c) {      // 32 columns per round: two TMEM loads in flight per wait
@@ -609,6 +690,19 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
             aux_prefetch<AUXB>(pre, p.aux, p.ldaux, row0, col + 32, p.M, p.N);       // during this round's math+stores
         }
         tmem_ld_wait();
+        if (wsp != nullptr) {
+          for (int j = 0; j < p.tail_s - 1; ++j) {
+            const float* pj = wsp + (size_t)j * (2 * NUM_EPI_WARPS) * 4096 + c * 1024;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint4 u = ld_global_cg_v4(pj + i * 128);
+              acc[4 * i] = __float_as_uint(__uint_as_float(acc[4 * i]) + __uint_as_float(u.x));
+              acc[4 * i + 1] = __float_as_uint(__uint_as_float(acc[4 * i + 1]) + __uint_as_float(u.y));
+              acc[4 * i + 2] = __float_as_uint(__uint_as_float(acc[4 * i + 2]) + __uint_as_float(u.z));
+              acc[4 * i + 3] = __float_as_uint(__uint_as_float(acc[4 * i + 3]) + __uint_as_float(u.w));
+            }
+          }
+        }
         if (live) epilogue32<EPI>(p, gate_t, stage_addr, row0, col, acc, aux_row);
       }
       tc_fence_before();
@@ -731,7 +825,8 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
     if (e != cudaSuccess) return ofk_set_error(OFK_ERR_CUDA, cudaGetErrorString(e));
     attr_done = true;
   }
-  const int work = ((p.M + 255) / 256) * ((p.N + 255) / 256) * p.splits;
+  const int tiles2 = ((p.M + 255) / 256) * ((p.N + 255) / 256);
+  const int work = p.tail_s > 0 ? p.tail_first + (tiles2 - p.tail_first) * p.tail_s : tiles2 * p.splits;
   int clusters = g_num_sms / 2;
   if (work < clusters) clusters = work;
   kern<<<2 * clusters, NUM_THREADS, Smem2::TOTAL, stream>>>(ta, tb, p);
@@ -796,11 +891,23 @@ static int dispatch_epi(int epi, int a_mn, int b_mn, const CUtensorMap& ta, cons
 
 }  // namespace ofk
 
+// Tail-split workspace: 4 KiB of per-warp flags (zero before first use; self-resetting) + one 256 x 256 fp32
+// partial per producer slice.  rem <= P / 2 = 37 tiles and rem * (s - 1) < P = 74 partials on a 148-SM part.
+constexpr int OFK_GEMM_WS_TILES = 74;
+constexpr long long OFK_GEMM_WS_FLAG_BYTES = 4096;
+constexpr long long OFK_GEMM_WS_BYTES = OFK_GEMM_WS_FLAG_BYTES + (long long)OFK_GEMM_WS_TILES * 256 * 256 * 4;
+constexpr int TAIL_MIN_KB = 48;   // below ~3k of K half a tile-time is not worth the partial round trip
+static bool tail_split_enabled() {
+  static int mode = -1;
+  if (mode < 0) { const char* e = getenv("OFK_GEMM_TAIL_SPLIT"); mode = e ? (atoi(e) != 0) : 1; }
+  return mode == 1;
+}
+
 static int gemm_impl(int epi, int a_mn_major, int b_mn_major, const void* A, long long lda, const void* B,
                      long long ldb, int M, int N, int K, int splits, int block_n, void* out, long long ldo,
                      void* out2, long long ldo2, const void* aux, long long ldaux, const float* bias,
                      const float* gate, void* stream_, int out_rpg, int out_gs, int out_go, int ak_rpg, int ak_gs,
-                     int ak_go) {
+                     int ak_go, void* workspace = nullptr, long long workspace_bytes = 0) {
   using namespace ofk;
   if (out_rpg > 0 && (epi != OFK_EPI_STORE_BF16 && epi != OFK_EPI_BIAS_BF16 && epi != OFK_EPI_STORE_F32))
     return ofk_set_error(OFK_ERR_ARG, "grouped output rows are supported by the STORE_BF16 / BIAS_BF16 / STORE_F32 epilogues");
@@ -835,6 +942,28 @@ static int gemm_impl(int epi, int a_mn_major, int b_mn_major, const void* A, lon
   p.splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
   p.out = out; p.ldo = ldo; p.out2 = out2; p.ldo2 = ldo2; p.aux = aux; p.ldaux = ldaux; p.bias = bias; p.gate = gate;
   p.out_rpg = out_rpg; p.out_gs = out_gs; p.out_go = out_go; p.ak_rpg = ak_rpg; p.ak_gs = ak_gs; p.ak_go = ak_go;
+  p.tail_first = 0; p.tail_s = 0; p.tail_kps = 0; p.tail_ws = nullptr; p.tail_flags = nullptr;
+  if (two_cta && p.splits == 1 && epi != OFK_EPI_ATOMIC_F32 && workspace != nullptr &&
+      workspace_bytes >= OFK_GEMM_WS_BYTES && tail_split_enabled() && total_kb >= TAIL_MIN_KB) {
+    // The persistent grid walks `tiles` 256 x 256 tiles on P SM pairs; when the last round is at most half full,
+    // cut its tiles into k-slices so that round costs 1/s of a tile-time (plus one fp32 partial round trip
+    // through L2) instead of a whole one: e.g. the N = 2048 GEMMs of MPT-1B are 256 tiles on 74 pairs = 3.46 rounds.
+    const int P = g_num_sms / 2;
+    const int tiles = ((M + 255) / 256) * ((N + 255) / 256);
+    const int rem = tiles % P;
+    if (rem > 0 && rem <= OFK_GEMM_WS_TILES / 2) {
+      int s_ = P / rem;
+      if (s_ > 4) s_ = 4;
+      if (s_ > total_kb / 16) s_ = total_kb / 16;
+      if (s_ >= 2 && rem * (s_ - 1) <= OFK_GEMM_WS_TILES) {
+        p.tail_first = tiles - rem;
+        p.tail_s = s_;
+        p.tail_kps = (total_kb + s_ - 1) / s_;
+        p.tail_flags = reinterpret_cast<int*>(workspace);
+        p.tail_ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + OFK_GEMM_WS_FLAG_BYTES);
+      }
+    }
+  }
   const int a_rows = ak_rpg > 0 ? (K / ak_rpg) * ak_gs : K;   // physical row count of an MN-major A
   {
     static int stream_mode = -1;   // OFK_GEMM_STREAM_OUT=0/1 overrides; default: stream when the outputs exceed ~32 MB
@@ -867,6 +996,16 @@ extern "C" int ofk_gemm_bf16(int epi, int a_mn_major, int b_mn_major, const void
                              const float* gate, void* stream_) {
   return gemm_impl(epi, a_mn_major, b_mn_major, A, lda, B, ldb, M, N, K, splits, block_n, out, ldo, out2, ldo2, aux, ldaux,
                    bias, gate, stream_, 0, 0, 0, 0, 0, 0);
+}
+
+extern "C" long long ofk_gemm_workspace_bytes(void) { return OFK_GEMM_WS_BYTES; }
+
+extern "C" int ofk_gemm_bf16_ws(int epi, int a_mn_major, int b_mn_major, const void* A, long long lda, const void* B,
+                                long long ldb, int M, int N, int K, int splits, int block_n, void* out, long long ldo,
+                                void* out2, long long ldo2, const void* aux, long long ldaux, const float* bias,
+                                const float* gate, void* workspace, long long workspace_bytes, void* stream_) {
+  return gemm_impl(epi, a_mn_major, b_mn_major, A, lda, B, ldb, M, N, K, splits, block_n, out, ldo, out2, ldo2, aux, ldaux,
+                   bias, gate, stream_, 0, 0, 0, 0, 0, 0, workspace, workspace_bytes);
 }
 
 extern "C" int ofk_gemm_bf16_grouped(int epi, int a_mn_major, int b_mn_major, const void* A, long long lda, const void* B,

@@ -52,11 +52,33 @@ def w16(param):
     return t
 
 
-def _wgrad_splits(m, n, k):
-    tiles = ((m + 127) // 128) * ((n + 255) // 256)
-    if tiles >= 148:
-        return 1
-    return max(1, min((k + 63) // 64, (148 + tiles - 1) // tiles))
+_SPLIT_CACHE = {}
+
+
+def _wgrad_splits(m, n, k, sms=148):
+    """Split-K factor for a wgrad [m, n] += dy^T x over k tokens (atomic epilogue, so any split is legal).
+    Mirrors the dispatcher in gemm_tcgen05.cu: 256 x 256 tiles on sms/2 SM pairs when m >= 512 and n >= 256, else
+    128 x {128,256} tiles on sms CTAs.  Picks the factor that minimises the number of tile-rounds the persistent
+    grid needs (ceil(tiles * s / units) / s): e.g. the FFN wgrads are 256 tiles on 74 pairs = 3.46 -> 4 rounds
+    unsplit, but 7 half-rounds = 3.5 with s = 2.  A small per-split charge stands for the extra fp32 reductions."""
+    key = (m, n, k)
+    s = _SPLIT_CACHE.get(key)
+    if s is not None:
+        return s
+    if m >= 512 and n >= 256:
+        tiles, units = ((m + 255) // 256) * ((n + 255) // 256), sms // 2
+    else:
+        bn = 256 if (n % 256 == 0 or n > 1024) else 128
+        tiles, units = ((m + 127) // 128) * ((n + bn - 1) // bn), sms
+    kb = (k + 63) // 64
+    best, best_cost = 1, None
+    for cand in range(1, min(16, max(1, kb // 4)) + 1):
+        rounds = -(-tiles * cand // units)
+        cost = rounds / cand + 0.03 * (cand - 1)
+        if best_cost is None or cost < best_cost - 1e-9:
+            best, best_cost = cand, cost
+    _SPLIT_CACHE[key] = best
+    return best
 
 
 class _GradSink:

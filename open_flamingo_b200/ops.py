@@ -17,6 +17,22 @@ def _rowmajor_2d(t, name):
         raise ValueError(f"{name} must be 2-D with unit inner stride, got shape {tuple(t.shape)} stride {t.stride()}")
 
 
+_gemm_ws = {}
+
+
+def _gemm_workspace(device):
+    """Scratch for the GEMM tail split (see ofk_gemm_bf16_ws): one buffer per (device, stream) so GEMMs that may
+    overlap never share it.  Allocated through torch's caching allocator, which is also legal while a CUDA graph
+    is being captured (the buffer then lives in the graph's private pool and is kept alive here)."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _gemm_ws.get(key)
+    if ws is None:
+        ws = torch.empty(int(L.lib().ofk_gemm_workspace_bytes()), device=device, dtype=torch.uint8)
+        ws[:4096].zero_()   # the flag words; they reset themselves after every use
+        _gemm_ws[key] = ws
+    return ws
+
+
 def gemm(a, b, *, a_mn=False, b_mn=False, epi=L.EPI_STORE_BF16, out=None, out2=None, aux=None, bias=None,
          gate=None, splits=1, block_n=0, M=None, N=None, K=None):
     """out[m,n] = epi(sum_k A(m,k) B(n,k)).
@@ -52,10 +68,12 @@ def gemm(a, b, *, a_mn=False, b_mn=False, epi=L.EPI_STORE_BF16, out=None, out2=N
         raise ValueError("gemm bias must be a contiguous float32 vector of length >= N")
     if gate is not None and gate.dtype != f32:
         raise ValueError("gemm gate must be float32")
-    L.check(L.lib().ofk_gemm_bf16(
+    ws = _gemm_workspace(a.device) if (splits == 1 and M >= 512 and N >= 256 and K >= 3072) else None
+    L.check(L.lib().ofk_gemm_bf16_ws(
         epi, int(a_mn), int(b_mn), a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), M, N, K, splits, block_n,
         out.data_ptr(), out.stride(0), L.ptr(out2), 0 if out2 is None else out2.stride(0),
-        L.ptr(aux), 0 if aux is None else aux.stride(0), L.ptr(bias), L.ptr(gate), L.stream_ptr()))
+        L.ptr(aux), 0 if aux is None else aux.stride(0), L.ptr(bias), L.ptr(gate),
+        L.ptr(ws), 0 if ws is None else ws.numel(), L.stream_ptr()))
     return out
 
 

@@ -85,6 +85,38 @@ def test_gemm_epilogues(ops, L):
     close(h, torch.nn.functional.gelu(acc.to(bf16).float()), tol, "gelu h 2cta")
 
 
+@pytest.mark.parametrize("M,N,K", [(2560, 2048, 4096), (2500, 2048, 3072), (512, 2048, 8192), (8192, 2048, 3072)])
+def test_gemm_tail_split_is_exact_and_epilogue_agnostic(ops, L, M, N, K):
+    """Shapes whose last round of 256 x 256 tiles fills at most half of the 74 SM pairs take the tail split
+    (k-slices of the last tiles exchange fp32 partials through the workspace, ofk_gemm_bf16_ws).  Integer operands
+    make every partial sum exact, so the result must be bit-identical to the unsplit product; the fused epilogues
+    must see the completed sum; repeated launches reuse the self-resetting flags."""
+    g = torch.Generator(device="cuda").manual_seed(21)
+    a = torch.randint(-3, 4, (M, K), device="cuda", generator=g).float()
+    b = torch.randint(-3, 4, (N, K), device="cuda", generator=g).float()
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        ref = a @ b.t()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    a16, b16 = a.to(bf16), b.to(bf16)
+    for _ in range(3):
+        assert torch.equal(ops.gemm(a16, b16, epi=L.EPI_STORE_F32), ref)
+    assert torch.equal(ops.gemm(a16, b16, epi=L.EPI_STORE_F32, block_n=256), ref)      # 1-CTA kernel: never split
+    assert torch.equal(ops.gemm(a16.t().contiguous(), b16.t().contiguous(), a_mn=True, b_mn=True, epi=L.EPI_STORE_F32), ref)
+    resid = torch.randint(-8, 9, (M, N), device="cuda", generator=g).float()
+    bias = torch.randint(-8, 9, (N,), device="cuda", generator=g).float()
+    o = ops.gemm(a16, b16, epi=L.EPI_BIAS_RESID_F32, aux=resid, bias=bias)
+    assert torch.equal(o, (ref + bias).to(bf16).float() + resid)
+    z = torch.empty(M, N, device="cuda", dtype=bf16)
+    h = torch.empty(M, N, device="cuda", dtype=bf16)
+    small = (a16 * 0.125).to(bf16), (b16 * 0.125).to(bf16)                              # keep GELU inputs O(1..10)
+    ops.gemm(*small, epi=L.EPI_GELU_DUAL, out=z, out2=h)
+    assert torch.equal(z, (ref / 64).to(bf16))
+    close(h, torch.nn.functional.gelu((ref / 64).to(bf16).float()), 1e-2, "gelu after tail split")
+
+
 def test_gemm_many_tiles_persistent(ops, L):
     """More tiles than SMs: exercises the persistent loop, smem-ring and TMEM double-buffer phase wraps."""
     torch.manual_seed(12)
