@@ -85,7 +85,7 @@ def test_gemm_epilogues(ops, L):
     close(h, torch.nn.functional.gelu(acc.to(bf16).float()), tol, "gelu h 2cta")
 
 
-@pytest.mark.parametrize("M,N,K", [(2560, 2048, 4096), (2500, 2048, 3072), (512, 2048, 8192), (8192, 2048, 3072)])
+@pytest.mark.parametrize("M,N,K", [(2560, 2048, 4096), (2496, 2048, 3072), (512, 2048, 8192), (8192, 2048, 3072)])
 def test_gemm_tail_split_is_exact_and_epilogue_agnostic(ops, L, M, N, K):
     """Shapes whose last round of 256 x 256 tiles fills at most half of the 74 SM pairs take the tail split
     (k-slices of the last tiles exchange fp32 partials through the workspace, ofk_gemm_bf16_ws).  Integer operands
