@@ -175,6 +175,15 @@ int ofk_attn_dense_bwd(const void* q, const void* k, const void* v, const void* 
 int ofk_text_time(const long long* input_ids, long long media_token_id, int batch, int t_txt, int n_loc,
                   const unsigned char* media_locations, int use_cached_media, int* text_time, void* stream);
 
+/* Training labels on the device (train_utils.py:102-106 for image-text pairs, :126-149 for interleaved MMC4 rows):
+ * labels = input_ids with pad_token_id and media_token_id replaced by -100; with interleaved != 0 also every token
+ * before the row's first <image> and every token after an <|endofchunk|> up to the next <image> (the
+ * <|endofchunk|> keeps its label).  Replaces the reference's per-row Python while-loops; int64 in / out,
+ * row strides in elements, rows independent; bit-exact. */
+int ofk_make_labels(const long long* input_ids, long long ld_ids, int batch, int t_txt, long long pad_token_id,
+                    long long media_token_id, long long endofchunk_token_id, int interleaved, long long* labels,
+                    long long ld_labels, void* stream);
+
 /* dst(bf16) = src(f32), n elements (n % 8 == 0 fast path). */
 int ofk_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);
 

@@ -40,6 +40,48 @@ __global__ void text_time_kernel(const long long* __restrict__ ids, long long me
   }
 }
 
+// ---- training labels (train_utils.py:102-106 LAION, :126-149 MMC4) ------------------------------------------
+// labels = input_ids with pad and <image> masked to -100; interleaved (MMC4) rows additionally mask every token
+// before the first <image> and every token between an <|endofchunk|> and the next <image> (the <|endofchunk|>
+// itself keeps its label).  The reference walks each row with Python while-loops; here it is a two-state scan
+// ("open" after an <image>, "closed" after an <|endofchunk|>, closed initially): 256 tokens per pass, coalesced,
+// the state a token sees = the kind of the latest <image>/<|endofchunk|> strictly before it (ballot + clz inside a
+// warp, 8 warp summaries in shared memory, a block-uniform carry between passes).
+__global__ void __launch_bounds__(256) make_labels_kernel(const long long* __restrict__ ids, long long ld_ids, int T,
+                                                          long long pad_id, long long media_id, long long eoc_id,
+                                                          int interleaved, long long* __restrict__ labels,
+                                                          long long ld_lab) {
+  __shared__ int s_last[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long* src = ids + (long long)blockIdx.x * ld_ids;
+  long long* dst = labels + (long long)blockIdx.x * ld_lab;
+  int carry = 0;   // 1 = open: the latest marker so far was an <image>
+  for (int t0 = 0; t0 < T; t0 += 256) {
+    const int t = t0 + tid;
+    const long long id = t < T ? src[t] : pad_id;
+    // the reference compares against the labels AFTER pad masking (train_utils.py:127-128), so a marker id that
+    // coincides with the pad id is never seen as a marker
+    int kind = 0;
+    if (t < T && id != pad_id) kind = (id == media_id) ? 1 : ((id == eoc_id) ? 2 : 0);
+    const unsigned nz = __ballot_sync(0xffffffffu, kind != 0);
+    const unsigned below = nz & ((1u << lane) - 1u);
+    const int prev = __shfl_sync(0xffffffffu, kind, below ? 31 - __clz(below) : 0);
+    int st = below ? prev : 0;                                   // 0 = no marker earlier in this warp
+    if (lane == 31) s_last[warp] = kind != 0 ? kind : st;        // latest marker of the whole warp
+    __syncthreads();
+    for (int w = warp - 1; w >= 0 && st == 0; --w) st = s_last[w];
+    int tile_last = 0;
+    for (int w = 7; w >= 0 && tile_last == 0; --w) tile_last = s_last[w];
+    const bool open = st == 0 ? (carry != 0) : (st == 1);
+    if (t < T) {
+      const bool masked = id == pad_id || id == media_id || (interleaved && !open);
+      dst[t] = masked ? -100LL : id;
+    }
+    if (tile_last != 0) carry = tile_last == 1;
+    __syncthreads();
+  }
+}
+
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
   const long long n8 = n / 8;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -199,6 +241,18 @@ extern "C" int ofk_text_time(const long long* input_ids, long long media_token_i
   if (batch <= 0 || t_txt <= 0) return 0;
   text_time_kernel<<<batch, 32, 0, (cudaStream_t)stream>>>(input_ids, media_token_id, t_txt, n_loc, media_locations,
                                                            use_cached_media, text_time);
+  OFK_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int ofk_make_labels(const long long* input_ids, long long ld_ids, int batch, int t_txt, long long pad_token_id,
+                               long long media_token_id, long long endofchunk_token_id, int interleaved,
+                               long long* labels, long long ld_labels, void* stream) {
+  if (batch <= 0 || t_txt <= 0) return 0;
+  if (!input_ids || !labels) return ofk_set_error(OFK_ERR_ARG, "make_labels: null pointer");
+  if (ld_ids < t_txt || ld_labels < t_txt) return ofk_set_error(OFK_ERR_ARG, "make_labels: row stride shorter than the row");
+  make_labels_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(input_ids, ld_ids, t_txt, pad_token_id, media_token_id,
+                                                              endofchunk_token_id, interleaved, labels, ld_labels);
   OFK_CHECK_LAUNCH();
   return 0;
 }

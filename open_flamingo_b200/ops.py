@@ -191,6 +191,25 @@ def attn_bwd(q, k, v, o, d_o, lse, heads, scale, *, mask_mode=L.MASK_NONE, text_
     return dq, dk, dv
 
 
+def make_labels(input_ids, pad_token_id, media_token_id, endofchunk_token_id=None, interleaved=False, out=None):
+    """Device-side training labels (train_utils.py:102-106; interleaved=True: the MMC4 rule of :126-149).
+    input_ids: int64 [B, T] on the GPU (row stride free).  Returns int64 [B, T]."""
+    L.require_cuda(input_ids)
+    if input_ids.dtype != torch.int64 or input_ids.dim() != 2 or (input_ids.numel() and input_ids.stride(1) != 1):
+        raise ValueError("make_labels expects an int64 [B, T] tensor with contiguous rows")
+    if interleaved and endofchunk_token_id is None:
+        raise ValueError("interleaved labels need the <|endofchunk|> token id")
+    B, T = input_ids.shape
+    if out is None:
+        out = torch.empty((B, T), device=input_ids.device, dtype=torch.int64)
+    if B == 0 or T == 0:
+        return out
+    L.check(L.lib().ofk_make_labels(input_ids.data_ptr(), input_ids.stride(0), B, T, int(pad_token_id),
+                                    int(media_token_id), int(-1 if endofchunk_token_id is None else endofchunk_token_id),
+                                    int(bool(interleaved)), out.data_ptr(), out.stride(0), L.stream_ptr()))
+    return out
+
+
 def text_time(input_ids=None, media_token_id=0, media_locations=None, use_cached_media=False, t_txt=None):
     """int32 [B, T_txt] inclusive count of media tokens (helpers.py:199-208)."""
     src = media_locations if media_locations is not None else input_ids

@@ -44,6 +44,25 @@ def hot_path_parameters(model):
     return groups
 
 
+def mask_embedding_grad(model, media_token_id=None, endofchunk_token_id=None, rows=None):
+    """With trainable LM input embeddings the reference lets only the two ADDED tokens learn: after backward it
+    multiplies the embedding gradient by a mask that is one on the `<image>` and `<|endofchunk|>` rows and zero
+    elsewhere, before clipping (train_utils.py:172-194).  In place; returns the gradient (or None).  `rows`: optional
+    device tensor holding the two row indices (avoids a host-to-device copy, e.g. under CUDA-graph capture)."""
+    emb = model.lang_encoder.get_input_embeddings()
+    g = emb.weight.grad
+    if g is None:
+        return None
+    media = model.media_token_id if media_token_id is None else media_token_id
+    eoc = model.eoc_token_id if endofchunk_token_id is None else endofchunk_token_id
+    if rows is None:
+        rows = torch.tensor([int(media), int(eoc)], device=g.device)
+    keep = g.index_select(0, rows)
+    g.zero_()
+    g.index_copy_(0, rows, keep)
+    return g
+
+
 class GradBucket:
     """Flat gradient (and optionally parameter) storage with chunked asynchronous all-reduce."""
 
@@ -182,6 +201,10 @@ class FlatTrainer:
         flat_ids = {id(p) for _, p, _, _ in b.entries}
         self.extra = [p for p in model.parameters() if p.requires_grad and id(p) not in flat_ids]
         self.extra_opt = torch.optim.AdamW(self.extra, lr=lr, betas=betas, eps=eps, weight_decay=0.0) if self.extra else None
+        emb_w = model.lang_encoder.get_input_embeddings().weight
+        self.mask_embeddings = any(p is emb_w for p in self.extra)   # train_utils.py:172-194
+        self._embed_rows = torch.tensor([int(model.media_token_id), int(model.eoc_token_id)], device=b.device) \
+            if self.mask_embeddings else None
         self.step_count = 0
         # device-resident step counter and learning rate: a captured CUDA graph of the step stays valid as they change
         self.step_dev = torch.zeros(1, device=b.device, dtype=torch.float32)
@@ -198,6 +221,8 @@ class FlatTrainer:
         b, ops = self.bucket, self.ops
         b.finish()
         world = b.world
+        if self.mask_embeddings:
+            mask_embedding_grad(self.model, rows=self._embed_rows)
         if self.extra and world > 1:
             for p in self.extra:
                 if p.grad is not None:

@@ -20,6 +20,30 @@ import torch
 import torch.nn.functional as F
 
 
+# ---------------------------------------------------------------------------------------------- labels
+def make_labels(input_ids, pad_token_id, media_token_id, endofchunk_token_id=None, interleaved=False):
+    """Training labels exactly as the reference's training loop builds them (open_flamingo/train/train_utils.py;
+    NOT under src/): :102-106 for image-text pairs, :126-149 for interleaved rows -- a literal, loop-for-loop
+    restatement (pure-Python, small cases only).  Pinned by tests/golden/labels.pt, which holds the tensors the
+    unmodified `train_one_epoch` handed to the model (tests/golden/make_golden_labels.py)."""
+    labels = input_ids.clone()
+    labels[labels == pad_token_id] = -100                                   # :104 / :127
+    if interleaved:
+        B, T = labels.shape
+        for i in range(B):
+            j = 0
+            while j < T and labels[i, j] != media_token_id:                 # :129-136 nothing before the first <image>
+                labels[i, j] = -100
+                j += 1
+            for e in torch.where(labels[i] == endofchunk_token_id)[0].tolist():   # :139 (positions taken up front)
+                j = e + 1
+                while j < T and labels[i, j] != media_token_id:             # :141-147 nothing between eoc and <image>
+                    labels[i, j] = -100
+                    j += 1
+    labels[labels == media_token_id] = -100                                 # :105 / :149
+    return labels
+
+
 # ---------------------------------------------------------------------------------------------- helpers
 def _ln(x, sd, prefix, eps=1e-5):
     return F.layer_norm(x, (x.shape[-1],), sd[prefix + ".weight"], sd[prefix + ".bias"], eps)

@@ -78,3 +78,25 @@ def test_graphed_step_equals_eager_step():
     b2["vision_x"] = torch.randn_like(b2["vision_x"])
     l_new = g(b2).item()
     assert l_new == l_new and abs(l_new - losses_graph[-1]) > 0
+
+
+def test_trainable_embeddings_only_update_the_two_added_tokens():
+    """freeze_lm_embeddings=False (the reference default): the embedding gradient is masked to the <image> and
+    <|endofchunk|> rows before clipping (train_utils.py:172-194), so every other row must stay bit-identical."""
+    from open_flamingo_b200.testing import build_flamingo, synthetic_batch
+    from open_flamingo_b200.train import FlatTrainer
+    model, _, tok = build_flamingo(VIT, MPT, device="cuda", gate_init=1.0, seed=3, freeze_lm_embeddings=False)
+    model.train()
+    media_id, eoc_id = tok.encode("<image>")[-1], tok.encode("<|endofchunk|>")[-1]
+    batch = {k: v.cuda() for k, v in synthetic_batch(3, 2, 24, media_id, eoc_id, 61, image_size=56, seed=9).items()}
+    emb = model.lang_encoder.get_input_embeddings().weight
+    assert emb.requires_grad
+    before = emb.detach().clone()
+    trainer = FlatTrainer(model, lr=1e-2, weight_decay=0.1, max_grad_norm=1.0)
+    assert trainer.mask_embeddings
+    for _ in range(2):
+        trainer.zero_grad()
+        fwd_bwd(model, batch)
+        trainer.step()
+    changed = (emb.detach() != before).any(1).nonzero().flatten().tolist()
+    assert changed == sorted([media_id, eoc_id]), changed
