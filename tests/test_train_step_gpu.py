@@ -100,3 +100,41 @@ def test_trainable_embeddings_only_update_the_two_added_tokens():
         trainer.step()
     changed = (emb.detach() != before).any(1).nonzero().flatten().tolist()
     assert changed == sorted([media_id, eoc_id]), changed
+
+
+def test_checkpoint_resume_continues_the_same_trajectory(tmp_path):
+    """save_checkpoint / load_checkpoint (reference format, train_utils.py:337-375 / train.py:297-308) restore
+    parameters, flat AdamW moments, step count and the bf16 operand copies: the step after a resume reproduces
+    the step of the uninterrupted run."""
+    import os
+    from open_flamingo_b200.checkpoint import load_checkpoint, save_checkpoint
+    from open_flamingo_b200.train import FlatTrainer
+    m1, batch = build(seed=4)
+    t1 = FlatTrainer(m1, lr=1e-3, weight_decay=0.1, max_grad_norm=1.0)
+    for _ in range(2):
+        t1.zero_grad()
+        fwd_bwd(m1, batch)
+        t1.step()
+    path = os.path.join(tmp_path, "checkpoint_0.pt")
+    save_checkpoint(path, m1, t1, epoch=0)
+    t1.zero_grad()
+    l_ref = fwd_bwd(m1, batch)
+    t1.step()
+    t1.zero_grad()
+    l_ref2 = fwd_bwd(m1, batch)
+
+    m2, _ = build(seed=4)
+    with torch.no_grad():                                   # start from different weights: everything must come from disk
+        for p in m2.parameters():
+            if p.requires_grad:
+                p.add_(0.05)
+    t2 = FlatTrainer(m2, lr=1e-3, weight_decay=0.1, max_grad_norm=1.0)
+    assert load_checkpoint(path, m2, t2) == 1
+    assert t2.step_count == 2
+    t2.zero_grad()
+    l_new = fwd_bwd(m2, batch)
+    t2.step()
+    t2.zero_grad()
+    l_new2 = fwd_bwd(m2, batch)
+    assert abs(l_new.item() - l_ref.item()) <= 1e-4 * abs(l_ref.item()), (l_new.item(), l_ref.item())
+    assert abs(l_new2.item() - l_ref2.item()) <= 2e-3 * abs(l_ref2.item()), (l_new2.item(), l_ref2.item())
