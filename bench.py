@@ -26,7 +26,12 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 VIT_L14 = dict(image_size=224, patch_size=14, width=1024, layers=24, heads=16, output_dim=768)
-METRIC = "OF-3B training tokens/sec"
+METRIC = "OF-3B training tokens/sec"          # BASELINE.json's metric (the default --model of3b)
+LM_NAME = {"of3b": "MPT-1B", "of9b": "MPT-7B"}
+
+
+def metric_name(model):
+    return METRIC if model == "of3b" else f"{model.upper().replace('OF', 'OF-')} training tokens/sec"
 UNIT = "tokens/s"
 
 
@@ -261,7 +266,7 @@ def run_reference(args):
     if rank != 0:
         return
     cb, dt = time_cpu_oracle(args.model, args.cpu_sample_batch, args.t_img, args.t_txt, args.steps, args.warmup)
-    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": metric_name(args.model), "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.model.upper()} train step (CPU port of the reference, oracle/)",
@@ -422,10 +427,10 @@ def run_ours(args):
                 cpu_baseline, _ = time_cpu_oracle(args.model, args.cpu_sample_batch, T_img, T_txt, steps=1, warmup=0)
             except Exception as e:  # pragma: no cover
                 cpu_baseline = {"error": repr(e)}
-        line = {"metric": METRIC, "value": tokens / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        line = {"metric": metric_name(args.model), "value": tokens / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": f"{args.model.upper()} (ViT-L/14 + MPT-1B-shaped HF MptForCausalLM, xattn_every={every}) "
+                "config": {"workload": f"{args.model.upper()} (ViT-L/14 + {LM_NAME.get(args.model, 'tiny')}-shaped HF MptForCausalLM, xattn_every={every}) "
                                        "amp_bf16 train step: fwd+bwd+grad all-reduce+clip+AdamW",
                            "global_batch": world * B, "per_gpu_batch": B, "t_img": T_img, "seq_len": T_txt,
                            "parallelism": f"dp{world}", "frozen_lm_blocks": args.lm, "cuda_graph": graphed is not None, "l2": "per-step working set (>10 GB weights+activations) exceeds the 126 MB L2; no explicit flush",
