@@ -167,6 +167,15 @@ int ofk_attn_dense_bwd(const void* q, const void* k, const void* v, const void* 
                        long long dv_bstride, long long lddv, float scale, int causal, const unsigned char* mask,
                        const float* slopes, const int* pure_causal_flag, void* stream);
 
+/* EXPERIMENTAL: ofk_attn_fwd on the tcgen05 tensor cores (TMA-staged Q/K/V tiles, S and O_j in TMEM, P through
+ * swizzled shared memory) -- same arguments, semantics and outputs as ofk_attn_fwd; additionally requires
+ * batch strides == rows * row stride.  Not validated on hardware yet and not used by any default path
+ * (ops.attn_fwd selects it only with OFK_ATTN_TC=1). */
+int ofk_attn_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse, int batch, int heads, int nq,
+                    int nk, long long q_bstride, long long ldq, long long k_bstride, long long ldk, long long v_bstride,
+                    long long ldv, long long o_bstride, long long ldo, float scale, int mask_mode,
+                    const int* text_time, int keys_per_media, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Small fused elementwise / reduction kernels.
  */

@@ -891,6 +891,11 @@ static int dispatch_epi(int epi, int a_mn, int b_mn, const CUtensorMap& ta, cons
 
 }  // namespace ofk
 
+int ofk_tensor_map_bf16(const void* ptr, long long ld, int rows, int cols, int box_inner, int box_outer,
+                        struct CUtensorMap_st* out) {
+  return ofk::get_tensor_map(ptr, ld, rows, cols, box_inner, box_outer, out);
+}
+
 // Tail-split workspace: 4 KiB of per-warp flags (zero before first use; self-resetting) + one 256 x 256 fp32
 // partial per producer slice.  rem <= P / 2 = 37 tiles and rem * (s - 1) < P = 74 partials on a 148-SM part.
 constexpr int OFK_GEMM_WS_TILES = 74;

@@ -4,6 +4,8 @@ These do no math of their own.  Argument-shape violations raise ValueError/Asser
 call (mirroring the reference's conventions, e.g. helpers.py:175-178); nonzero return codes from the
 library become RuntimeError.
 """
+import os
+
 import torch
 
 from . import _lib as L
@@ -135,6 +137,9 @@ def _bstride_ld(t, name):
     return t.stride(0), t.stride(1)
 
 
+_ATTN_TC = os.environ.get("OFK_ATTN_TC", "0") == "1"
+
+
 def attn_fwd(q, k, v, heads, scale, *, mask_mode=L.MASK_NONE, text_time=None, keys_per_media=64, out=None,
              want_lse=True):
     """q: [B, nq, heads*64] (may be a column-slice view), k/v: [B, nk, heads*64].  Returns (o, lse)."""
@@ -154,9 +159,14 @@ def attn_fwd(q, k, v, heads, scale, *, mask_mode=L.MASK_NONE, text_time=None, ke
         if text_time is None or text_time.dtype != torch.int32 or tuple(text_time.shape) != (B, nq):
             raise ValueError("media mask needs int32 text_time of shape [B, nq]")
         text_time = text_time.contiguous()
-    L.check(L.lib().ofk_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), L.ptr(lse), B, heads, nq, nk,
-                                 qb, ldq, kb, ldk, vb, ldv, ob, ldo, scale, mask_mode, L.ptr(text_time), keys_per_media,
-                                 L.stream_ptr()))
+    # OFK_ATTN_TC=1 selects the EXPERIMENTAL tcgen05 forward core (attention_tc.cu; not validated on hardware yet)
+    # for the layouts it supports; every default path uses the mma.sync kernel of attention.cu.
+    fn = L.lib().ofk_attn_fwd
+    if _ATTN_TC and qb == nq * ldq and kb == nk * ldk and vb == nk * ldv and ldo % 8 == 0 and ob % 8 == 0 and \
+            (mask_mode == L.MASK_NONE or (keys_per_media % 16 == 0 and nk % keys_per_media == 0)):
+        fn = L.lib().ofk_attn_fwd_tc
+    L.check(fn(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), L.ptr(lse), B, heads, nq, nk,
+               qb, ldq, kb, ldk, vb, ldv, ob, ldo, scale, mask_mode, L.ptr(text_time), keys_per_media, L.stream_ptr()))
     return out, lse
 
 
