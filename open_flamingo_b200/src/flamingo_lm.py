@@ -17,6 +17,13 @@ from .utils import getattr_recursive, setattr_recursive
 
 
 class FlamingoLayer(nn.Module):
+    """One decoder position: optional gated cross-attention block, then the frozen decoder block
+    (flamingo_lm.py:6-66).  State set from outside before each forward, exactly as in the reference:
+      vis_x            (B, T_img, n_latents, D_vis) resampler output, shared by all layers (`condition_vis_x`)
+      media_locations  (B, T_txt) bool, True at `<image>` tokens (`condition_media_locations`)
+      use_cached_media bool, decode-time switch: every text token attends the last cached image
+    The attribute names `gated_cross_attn_layer` / `decoder_layer` are part of the checkpoint key names."""
+
     def __init__(self, gated_cross_attn_layer, decoder_layer, gradient_checkpointing=False):
         super().__init__()
         self.gated_cross_attn_layer = gated_cross_attn_layer
@@ -34,8 +41,10 @@ class FlamingoLayer(nn.Module):
         decoder_layer._use_gradient_checkpointing = gradient_checkpointing
 
     def is_conditioned(self) -> bool:
+        """True once both the visual features and the media locations are in place (flamingo_lm.py:28-30)."""
         return self.vis_x is not None and self.media_locations is not None
 
+    # the three setters below are called per forward by Flamingo / FlamingoLMMixin (flamingo_lm.py:33-41)
     def condition_vis_x(self, vis_x):
         self.vis_x = vis_x
 
@@ -46,6 +55,9 @@ class FlamingoLayer(nn.Module):
         self.use_cached_media = use_cached_media
 
     def forward(self, lang_x, attention_mask=None, **decoder_layer_kwargs):
+        """lang_x (B, T_txt, D) -> whatever the wrapped decoder block returns (flamingo_lm.py:43-66).  The gated
+        block runs on libofk (fused.GatedXattnBlockFn); a recognised frozen block too (lm_blocks.FrozenMptBlockFn),
+        falling back to the block's own PyTorch forward whenever the fast path declines (KV cache, dropout, ...)."""
         xattn = self.gated_cross_attn_layer
         if xattn is not None:
             # same failure modes as the reference (flamingo_lm.py:47-53)
@@ -67,6 +79,8 @@ class FlamingoLMMixin(nn.Module):
     """Mixed into a HF causal LM instance with utils.extend_instance (factory.py:85)."""
 
     def set_decoder_layers_attr_name(self, decoder_layers_attr_name):
+        """Dotted path of the decoder's nn.ModuleList inside the HF model, e.g. "transformer.blocks" for MPT
+        (factory.py:86,132-141)."""
         self.decoder_layers_attr_name = decoder_layers_attr_name
 
     def _get_decoder_layers(self):
@@ -97,6 +111,9 @@ class FlamingoLMMixin(nn.Module):
         self._set_decoder_layers(nn.ModuleList([FlamingoLayer(x, blk, gradient_checkpointing) for x, blk in pairs]))
 
     def forward(self, input_ids, attention_mask, **kwargs):
+        """Derive media_locations from the ids, push the conditioning into every layer, then run the HF model's own
+        forward (flamingo_lm.py:127-155).  Additions that do not change results: the device-side all-ones flag for
+        the attention kernel and the capture-safe 4-D mask (see below)."""
         if not getattr(self, "initialized_flamingo", False):
             raise ValueError("Flamingo layers are not initialized. Please call `init_flamingo` first.")
         media_locations = input_ids == self.media_token_id
@@ -129,9 +146,12 @@ class FlamingoLMMixin(nn.Module):
         return super().forward(input_ids=input_ids, attention_mask=attention_mask, **kwargs)
 
     def is_conditioned(self) -> bool:
+        """All layers hold vis_x and media_locations (flamingo_lm.py:157-159)."""
         return all(layer.is_conditioned() for layer in self._get_decoder_layers())
 
     def clear_conditioned_layers(self):
+        """Drop the per-forward state of every layer (flamingo_lm.py:161-167); Flamingo.forward calls this unless
+        `clear_conditioned_layers=False` (media cached for scoring, flamingo.py:118-119)."""
         for layer in self._get_decoder_layers():
             layer.condition_vis_x(None)
             layer.condition_media_locations(None)

@@ -1,4 +1,7 @@
-"""Small object-plumbing helpers with the reference's names (open_flamingo/src/utils.py:1-31)."""
+"""Small object-plumbing helpers with the reference's names (open_flamingo/src/utils.py:1-31).
+
+`apply_with_stopping_condition` (utils.py:34-48) is not provided: its only caller is the FSDP wrapper
+(flamingo.py:202-301), which is out of scope here."""
 from functools import reduce
 
 
@@ -20,15 +23,3 @@ def setattr_recursive(obj, att, val):
     """setattr_recursive(m, "a.b.c", v) sets m.a.b.c = v."""
     head, _, leaf = att.rpartition(".")
     setattr(getattr_recursive(obj, head), leaf, val)
-
-
-def apply_with_stopping_condition(module, apply_fn, apply_condition=None, stopping_condition=None, **other_args):
-    """Depth-first walk applying `apply_fn` where `apply_condition` holds, pruning subtrees at
-    `stopping_condition` (reference utils.py:34-48; used there only by the FSDP wrapper)."""
-    if stopping_condition is not None and stopping_condition(module):
-        return
-    if apply_condition is None or apply_condition(module):
-        apply_fn(module, **other_args)
-    for child in module.children():
-        apply_with_stopping_condition(child, apply_fn, apply_condition=apply_condition,
-                                      stopping_condition=stopping_condition, **other_args)
