@@ -129,6 +129,16 @@ def stream_ptr():
 
 
 def require_cuda(*tensors):
+    """Every tensor must live on the CURRENT CUDA device: kernels are enqueued on that device's current stream
+    (a model moved to cuda:1 without torch.cuda.set_device(1) would otherwise be launched on the wrong GPU)."""
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("open_flamingo_b200 kernels need CUDA tensors (sm_100a); there is no CPU path")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise RuntimeError(f"tensor on cuda:{t.device.index} but the current device is cuda:{cur}: call "
+                               "torch.cuda.set_device() (one process per GPU) before running the model")

@@ -55,7 +55,7 @@ def load_checkpoint(path_or_dict, model, trainer=None):
     if trainer is not None:
         if ckpt.get("optimizer_state_dict") is not None:
             load_flat_optimizer_state(trainer, ckpt["optimizer_state_dict"])
-        trainer.ops.cast_bf16(trainer.bucket.params, out=trainer.w16)
+        trainer.refresh_w16()
     return int(ckpt["epoch"]) + 1
 
 

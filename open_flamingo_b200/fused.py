@@ -40,7 +40,14 @@ def w16(param):
     The cache entry holds a weak reference to the parameter and is only trusted if it still points at THIS object
     (ids, versions and device addresses are all recycled once a parameter is freed)."""
     cached = getattr(param, "_ofk_w16", None)
-    if cached is not None:  # maintained by the fused AdamW kernel (train.FlatTrainer)
+    if cached is not None:
+        # Maintained by the fused AdamW kernel (train.FlatTrainer), which writes parameter and copy through raw
+        # pointers and so never bumps the version counter.  Anything else that changes the fp32 master --
+        # model.load_state_dict(...) after the trainer was built (the reference's resume path, train.py:297-308), a
+        # manual edit under no_grad -- does bump it: re-cast into the trainer's buffer before the GEMMs read it.
+        if getattr(param, "_ofk_w16_version", None) != param._version:
+            ops.cast_bf16(param.detach(), out=cached)
+            param._ofk_w16_version = param._version
         return cached
     key = id(param)
     ent = _w16_cache.get(key)
@@ -296,10 +303,13 @@ class PerceiverLayerFn(torch.autograd.Function):
         # d(kv_input): media rows feed only norm_media's affine grads (x itself is frozen), latent rows feed
         # norm_latents.
         dkv_in = ops.gemm(dkv, w16(wkv), b_mn=True)                                  # [U*(v+n), Dv] bf16
-        if sinks["nm_w"].needs or sinks["nm_b"].needs:
-            ops.layernorm_bwd(dkv_in, x2d, nm_w, xm_mean, xm_rstd, dgamma=sinks["nm_w"].buffer(),
-                              dbeta=sinks["nm_b"].buffer(), want_dx=False, rows_per_group=v, group_stride=v + n,
-                              group_offset=0)
+        dx_media = None
+        if sinks["nm_w"].needs or sinks["nm_b"].needs or needs[0]:
+            # needs[0]: the media tokens carry a gradient only when trainable frame / media-time embeddings were
+            # added to them (helpers.py:118-125); the frozen ViT features themselves never do (flamingo.py:194).
+            dx_media = ops.layernorm_bwd(dkv_in, x2d, nm_w, xm_mean, xm_rstd, dgamma=sinks["nm_w"].buffer(),
+                                         dbeta=sinks["nm_b"].buffer(), want_dx=bool(needs[0]), rows_per_group=v,
+                                         group_stride=v + n, group_offset=0)
         dlatn_q = ops.gemm(dq2, w16(wq), b_mn=True)                                  # [U*n, Dv] bf16
         dlat = ops.layernorm_bwd(dlatn_q, lat2d, nl_w, l_mean, l_rstd, dgamma=sinks["nl_w"].buffer(),
                                  dbeta=sinks["nl_b"].buffer(), dx_add=dlat1)
@@ -307,7 +317,8 @@ class PerceiverLayerFn(torch.autograd.Function):
                                  dbeta=sinks["nl_b"].buffer(), dx=dlat, dx_add=dlat, rows_per_group=n,
                                  group_stride=v + n, group_offset=v)
         grads = [sinks[nm].result() for nm in names]
-        return (None, dlat.view(U, n, Dv) if needs[1] else None, None, *grads)
+        return (dx_media.view(U, v, Dv) if (needs[0] and dx_media is not None) else None,
+                dlat.view(U, n, Dv) if needs[1] else None, None, *grads)
 
 
 class FinalNormFn(torch.autograd.Function):

@@ -121,6 +121,8 @@ class FastMptBlock:
         b = self.block
         if not ENABLED or not hidden_states.is_cuda or layer_past is not None or output_attentions:
             return False
+        if use_cache:
+            return False   # a caller that wants a `present` back (tuple-cache HF versions) gets the block's own forward
         a = b.attn
         if getattr(a, "clip_qkv", None) or (b.training and (a.attn_dropout_p > 0 or b.dropout_rate > 0 or
                                                             b.ffn.hidden_dropout > 0)):

@@ -35,6 +35,17 @@ def _gemm_workspace(device):
     return ws
 
 
+_comm_in_flight = False
+
+
+def set_comm_in_flight(flag):
+    """train.GradBucket brackets the window in which gradient-chunk all-reduces may be running.  Inside it the GEMM
+    tail split is not used: its owner slice spins on flags written by OTHER clusters of the same persistent grid,
+    which assumes all clusters are co-resident -- not guaranteed while NCCL's CTAs hold SMs."""
+    global _comm_in_flight
+    _comm_in_flight = bool(flag)
+
+
 def gemm(a, b, *, a_mn=False, b_mn=False, epi=L.EPI_STORE_BF16, out=None, out2=None, aux=None, bias=None,
          gate=None, splits=1, block_n=0, M=None, N=None, K=None):
     """out[m,n] = epi(sum_k A(m,k) B(n,k)).
@@ -70,7 +81,8 @@ def gemm(a, b, *, a_mn=False, b_mn=False, epi=L.EPI_STORE_BF16, out=None, out2=N
         raise ValueError("gemm bias must be a contiguous float32 vector of length >= N")
     if gate is not None and gate.dtype != f32:
         raise ValueError("gemm gate must be float32")
-    ws = _gemm_workspace(a.device) if (splits == 1 and M >= 512 and N >= 256 and K >= 3072) else None
+    ws = _gemm_workspace(a.device) if (splits == 1 and M >= 512 and N >= 256 and K >= 3072 and not _comm_in_flight) \
+        else None
     L.check(L.lib().ofk_gemm_bf16_ws(
         epi, int(a_mn), int(b_mn), a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), M, N, K, splits, block_n,
         out.data_ptr(), out.stride(0), L.ptr(out2), 0 if out2 is None else out2.stride(0),

@@ -25,7 +25,6 @@ _OPEN_CLIP_VISION_CFG = {
     "ViT-L-14-336": dict(image_size=336, patch_size=14, width=1024, layers=24, heads=16, output_dim=768),
     "ViT-B-16": dict(image_size=224, patch_size=16, width=768, layers=12, heads=12, output_dim=512),
     "ViT-B-32": dict(image_size=224, patch_size=32, width=768, layers=12, heads=12, output_dim=512),
-    "ViT-H-14": dict(image_size=224, patch_size=14, width=1280, layers=32, heads=20, output_dim=1024),
 }
 
 # decoder ModuleList attribute per LM family (reference factory.py:132-141)
@@ -84,11 +83,18 @@ def _build_vision(clip_vision_encoder_path, clip_vision_encoder_pretrained, cach
         ref_model, _, image_processor = open_clip.create_model_and_transforms(
             name, pretrained=clip_vision_encoder_pretrained, cache_dir=cache_dir)
         cfg = dict(open_clip.get_model_config(name)["vision_cfg"])
+        head_width = cfg.get("head_width", 64)
+        if head_width != 64:
+            raise ValueError(f"{name}: head_width {head_width} (open_clip vision_cfg) is not supported -- the sm_100a "
+                             "ViT attention kernel is built for head_dim 64 (ViT-B/L; ViT-H/g/bigG use 80-104)")
         ours = VisionTransformer(image_size=cfg.get("image_size", 224), patch_size=cfg["patch_size"],
-                                 width=cfg["width"], layers=cfg["layers"], heads=cfg["width"] // 64,
-                                 output_dim=ref_model.visual.proj.shape[1],
+                                 width=cfg["width"], layers=cfg["layers"], heads=cfg["width"] // head_width,
+                                 mlp_ratio=cfg.get("mlp_ratio", 4.0), output_dim=ref_model.visual.proj.shape[1],
                                  quick_gelu=clip_vision_encoder_pretrained == "openai")
-        ours.load_state_dict(ref_model.visual.state_dict(), strict=False)
+        missing, unexpected = ours.load_state_dict(ref_model.visual.state_dict(), strict=False)
+        if missing or unexpected:
+            raise KeyError(f"{name}: open_clip visual tower does not match this ViT implementation "
+                           f"(missing {sorted(missing)[:4]}, unexpected {sorted(unexpected)[:4]})")
         return CLIPVisionStandIn(ours), image_processor, cfg["width"]
     if name not in _OPEN_CLIP_VISION_CFG:
         raise ValueError(f"unknown CLIP vision config {name!r}; known: {sorted(_OPEN_CLIP_VISION_CFG)}")

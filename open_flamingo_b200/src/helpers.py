@@ -93,9 +93,10 @@ class PerceiverResampler(nn.Module):
         n = self.latents.shape[0]
         latents = self.latents.unsqueeze(0).expand(U, n, D)  # broadcast view; grads reduce back over U
         vtok = F * v
-        if vtok % 64 == 0 and D % 64 == 0:
+        if vtok % 64 == 0 and D % 64 == 0 and not x3.requires_grad:
             # the media tokens never change across layers: normalise them once and fold each layer's norm_media
-            # affine into its to_kv weights (fused.PerceiverFoldedLayerFn)
+            # affine into its to_kv weights (fused.PerceiverFoldedLayerFn).  With trainable frame / media-time
+            # embeddings (helpers.py:118-125) the media tokens DO need a gradient: the unfolded layer returns it.
             xa = fused.normalise_media(x3.view(U * vtok, D), self.layers[0][0].norm_media.eps)
             for attn, ff in self.layers:
                 latents = fused.PerceiverFoldedLayerFn.apply(

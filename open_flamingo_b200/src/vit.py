@@ -61,7 +61,7 @@ class VisionTransformer(nn.Module):
                  output_dim=768, quick_gelu=True, output_tokens=False):
         super().__init__()
         if width % heads != 0 or width // heads != 64:
-            raise ValueError("the sm_100a attention kernel needs head_dim == 64 (true for every CLIP ViT)")
+            raise ValueError("the sm_100a attention kernel needs head_dim == 64 (CLIP ViT-B / ViT-L; not ViT-H/g/bigG)")
         self.image_size, self.patch_size, self.width, self.heads = image_size, patch_size, width, heads
         self.grid = image_size // patch_size
         self.output_dim = output_dim

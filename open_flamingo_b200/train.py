@@ -21,7 +21,7 @@ import math
 import torch
 import torch.distributed as dist
 
-from . import fused
+from . import fused, ops
 
 ALIGN = 64  # elements; keeps every parameter view 256-byte (fp32) / 128-byte (bf16) aligned for TMA
 
@@ -121,6 +121,7 @@ class GradBucket:
             self._chunk_last_group[c] = max(self._chunk_last_group.get(c, -1), g)
         self._pending = []
         self._launched = set()
+        self._sync = True      # False inside no_sync(): gradients accumulate locally, nothing is reduced
 
     # -------------------------------------------------------------- distributed
     @property
@@ -130,8 +131,9 @@ class GradBucket:
         return dist.get_world_size(self.pg)
 
     def zero(self):
+        if self._pending:
+            raise RuntimeError("GradBucket.zero() with all-reduces still in flight: call finish() / step() first")
         self.grads.zero_()
-        self._pending = []
         self._launched = set()
 
     def _launch(self, c):
@@ -140,7 +142,30 @@ class GradBucket:
         self._launched.add(c)
         if self.world > 1:
             s, e = self.chunks[c]
+            # While a chunk is being reduced NCCL's CTAs and the persistent GEMM grid compete for SMs: the GEMM tail
+            # split (whose owner slice spins on flags written by other clusters of the same grid) is switched off
+            # for that window so no GEMM depends on co-residency of all its clusters.
+            ops.set_comm_in_flight(True)
             self._pending.append(dist.all_reduce(self.grads[s:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+
+    def no_sync(self):
+        """Context manager for gradient accumulation, with DDP.no_sync()'s meaning: backward passes run inside it
+        only ACCUMULATE into the flat buffer; no chunk is reduced.  The reference's optimizer step is several
+        backward passes (LAION batch, MMC4 batch, times gradient_accumulation_steps: train_utils.py:109-118,
+        :153-172, :206-216); run all but the last one under no_sync() and the chunk all-reduces are launched
+        (overlapped with the remaining backward) only during the final backward, when a chunk's contents are final."""
+        bucket = self
+
+        class _NoSync:
+            def __enter__(self_):
+                self_.prev = bucket._sync
+                bucket._sync = False
+
+            def __exit__(self_, *exc):
+                bucket._sync = self_.prev
+                return False
+
+        return _NoSync()
 
     def on_block_backward_done(self, params):
         """Called by fused.GatedXattnBlockFn.backward once a block's gradient kernels are enqueued."""
@@ -148,6 +173,15 @@ class GradBucket:
         if g is None:
             return
         c = self.group_to_chunk[g]
+        if c in self._launched and self.world > 1:
+            # a backward pass after this chunk's all-reduce was launched would add local gradients to a buffer that
+            # is already (being) reduced: ranks would silently diverge.  Make the mistake loud.
+            raise RuntimeError(
+                "GradBucket: a backward pass reached a gradient chunk whose all-reduce has already been launched in "
+                "this optimizer step.  Run every backward except the last under `trainer.no_sync()` (gradient "
+                "accumulation), and call zero_grad() after step().")
+        if not self._sync:
+            return
         if self._chunk_last_group[c] == g:   # groups complete in increasing g; the chunk's last group closes it
             self._launch(c)
 
@@ -159,6 +193,7 @@ class GradBucket:
         for w in self._pending:
             w.wait()
         self._pending = []
+        ops.set_comm_in_flight(False)
 
     def install_hooks(self):
         fused.block_backward_hook = self.on_block_backward_done
@@ -173,7 +208,6 @@ class FlatTrainer:
 
     def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.1, max_grad_norm=1.0,
                  num_chunks=6, process_group=None):
-        from . import ops
         self.ops = ops
         self.model = model
         self.lr, self.betas, self.eps, self.wd, self.max_norm = lr, betas, eps, weight_decay, max_grad_norm
@@ -188,6 +222,7 @@ class FlatTrainer:
         ops.cast_bf16(b.params, out=self.w16)
         for name, p, o, n in b.entries:
             p._ofk_w16 = self.w16[o:o + n].view(p.shape)
+            p._ofk_w16_version = p._version
         # weight-decay segment: the gated blocks come first in the layout (train.py:392-408 decays only them)
         self.decay_end = 0
         ei = 0
@@ -216,6 +251,10 @@ class FlatTrainer:
         self.bucket.zero()
         for p in self.extra:
             p.grad = None
+
+    def no_sync(self):
+        """Gradient accumulation (see GradBucket.no_sync): every backward of an optimizer step except the last."""
+        return self.bucket.no_sync()
 
     def step(self):
         b, ops = self.bucket, self.ops
@@ -256,6 +295,13 @@ class FlatTrainer:
             self.extra_opt.step()
         return norm
 
+    def refresh_w16(self):
+        """Re-cast every bf16 operand copy from the fp32 masters (fused.w16 also does this lazily, per parameter,
+        whenever a parameter's version counter shows it was modified outside the fused optimizer)."""
+        self.ops.cast_bf16(self.bucket.params, out=self.w16)
+        for name, p, o, n in self.bucket.entries:
+            p._ofk_w16_version = p._version
+
     def set_lr(self, lr):
         """Learning-rate schedule hook (train.py:434-450): updates the host value and the device scalar."""
         self.lr = float(lr)
@@ -273,8 +319,13 @@ class GraphedTrainStep:
     uncapturable collective, ...) `ok` is False and calls run the same step eagerly."""
 
     def __init__(self, model, trainer, example_batch, autocast_dtype=torch.bfloat16, warmup=3):
+        """example_batch: one batch dict, or a LIST of batch dicts = the micro-batches of one optimizer step (the
+        reference's step is a LAION backward + an MMC4 backward, train_utils.py:109-118,153-172): every micro-batch
+        but the last runs under trainer.no_sync(), so chunk all-reduces overlap the final backward only."""
         self.model, self.trainer, self.dtype = model, trainer, autocast_dtype
-        self.static = {k: v.clone() for k, v in example_batch.items()}
+        self.multi = isinstance(example_batch, (list, tuple))
+        batches = list(example_batch) if self.multi else [example_batch]
+        self.static = [{k: v.clone() for k, v in b.items()} for b in batches]
         self.ok = False
         self.error = None
         cur = torch.cuda.current_stream()
@@ -297,20 +348,33 @@ class GraphedTrainStep:
             self.graph = None
             torch.cuda.synchronize()
 
-    def _eager(self, batch):
-        self.trainer.zero_grad()
+    def _fwd_bwd(self, batch):
         with torch.autocast("cuda", dtype=self.dtype):
             out = self.model(vision_x=batch["vision_x"], lang_x=batch["lang_x"],
                              attention_mask=batch.get("attention_mask"), labels=batch["labels"])
         out.loss.backward()
-        self.trainer.step()
         return out.loss.detach()
 
+    def _eager(self, batches):
+        self.trainer.zero_grad()
+        loss = None
+        for i, batch in enumerate(batches):
+            if i + 1 < len(batches):
+                with self.trainer.no_sync():
+                    l = self._fwd_bwd(batch)
+            else:
+                l = self._fwd_bwd(batch)
+            loss = l if loss is None else loss + l
+        self.trainer.step()
+        return loss
+
     def __call__(self, batch):
+        batches = list(batch) if self.multi else [batch]
         if not self.ok:
-            return self._eager(batch)
-        for k, v in batch.items():
-            if v is not self.static[k]:
-                self.static[k].copy_(v, non_blocking=True)
+            return self._eager(batches)
+        for st, b in zip(self.static, batches):
+            for k, v in b.items():
+                if v is not st[k]:
+                    st[k].copy_(v, non_blocking=True)
         self.graph.replay()
         return self.loss

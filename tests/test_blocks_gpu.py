@@ -57,7 +57,16 @@ def test_perceiver_with_embeddings_and_many_tokens():
     m = PerceiverResampler(dim=fx["dim"], depth=fx["depth"], max_num_media=3, max_num_frames=2).cuda()
     m.load_state_dict(sd_cpu)
     x = seeded_tensor("perceiver_embs/x", fx["x_shape"], 2)
-    cmp(m(x.cuda()), fx["y"], OUT_TOL, "perceiver+embs vs golden")
+    y = m(x.cuda())
+    cmp(y, fx["y"], OUT_TOL, "perceiver+embs vs golden")
+    # the embeddings are trainable in the reference (helpers.py:118-125): their gradients must flow through the
+    # media rows of every layer's norm_media / to_kv
+    w = seeded_tensor("perceiver_embs/w", tuple(y.shape), 2)
+    (y * w.cuda()).sum().backward()
+    sd_req = {k: v.clone().requires_grad_(True) for k, v in sd_cpu.items()}
+    (O.perceiver_resampler(x, sd_req) * w).sum().backward()
+    for name in ("frame_embs", "media_time_embs", "latents"):
+        cmp(dict(m.named_parameters())[name].grad, sd_req[name].grad, GRAD_TOL, f"perceiver+embs d{name}")
     # longer media (ragged tile tail: v + n = 200 + 64 keys)
     torch.manual_seed(0)
     m2 = PerceiverResampler(dim=128, depth=1).cuda()
