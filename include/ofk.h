@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define OFK_ABI_VERSION 1
+#define OFK_ABI_VERSION 2
 
 enum {
   OFK_OK = 0,
@@ -118,9 +118,13 @@ int ofk_layernorm_bwd(const void* dy, int dy_is_f32, long long lddy, int rows_pe
 
 /* ------------------------------------------------------------------------------------------------
  * Attention core  O = softmax(scale * Q K^T + mask) V  per (batch, head), head_dim = 64, bf16 in/out,
- * fp32 softmax, online (flash-style), tensor-core MMA.
+ * fp32 softmax, online (flash-style).
+ * Default implementation (csrc/attention_tc.cu): Q/K/V (and dO) tiles staged by TMA (cp.async.bulk.tensor, 128-byte
+ * swizzle), QK^T / PV and the five backward contractions as tcgen05.mma with TMEM accumulators, lane-per-row softmax
+ * on the TMEM read-out, P / dS through swizzled shared memory.  It needs batch strides == rows * row stride and
+ * 16-byte aligned bases; any other layout runs the mma.sync kernels of csrc/attention.cu (same results).
  *   q: [batch, nq, heads*64] (ldq row stride), k/v: [batch, nk, heads*64] (ldk/ldv), o like q (ldo).
- *   q_bstride/k_bstride...: batch strides in elements.  lse: [batch, heads, nq] f32 (log-sum-exp, for bwd).
+ *   q_bstride/k_bstride...: batch strides in elements.  lse: [batch, heads, nq] f32 (log2 domain, for bwd).
  *   mask_mode: 0 = none                                              PerceiverAttention helpers.py:58-63, ViT MHA
  *              1 = media mask, text_time == block+1  (torch.eq)       MaskedCrossAttention helpers.py:196-229
  *              2 = media mask, text_time >= block+1  (torch.ge)       only_attend_immediate_media=False
@@ -133,18 +137,25 @@ int ofk_attn_fwd(const void* q, const void* k, const void* v, void* o, float* ls
                  long long v_bstride, long long ldv, long long o_bstride, long long ldo, float scale,
                  int mask_mode, const int* text_time, int keys_per_media, void* stream);
 
+/* Scratch the tensor-core backward needs: an fp32 dQ accumulator [batch*nq, heads*head_dim] whenever more than one
+ * 128-key tile contributes to a query row (0 bytes when nk <= 128).  Caller-owned, 16-byte aligned, need not be
+ * initialised.  Without it (NULL / too small) the backward runs the mma.sync kernels. */
+long long ofk_attn_bwd_workspace_bytes(int batch, int heads, int head_dim, int nq, int nk);
+
 /* Backward of the above.  delta: [batch, heads, nq] f32 scratch.  dq like q; dk/dv like k/v (bf16).
- * dk/dv are fully overwritten.  */
+ * dq/dk/dv are fully overwritten.  */
 int ofk_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                  float* delta, void* dq, void* dk, void* dv, int batch, int heads, int nq, int nk,
                  long long q_bstride, long long ldq, long long k_bstride, long long ldk, long long v_bstride,
                  long long ldv, long long o_bstride, long long ldo, long long dq_bstride, long long lddq,
                  long long dk_bstride, long long lddk, long long dv_bstride, long long lddv, float scale,
-                 int mask_mode, const int* text_time, int keys_per_media, void* stream);
+                 int mask_mode, const int* text_time, int keys_per_media, void* workspace, long long workspace_bytes,
+                 void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Dense self-attention core of the frozen LM's decoder blocks (HF MptAttention; reached via
- * flamingo_lm.py:63-65 -- SURVEY.md section 8f rank 1).  head_dim 64 or 128.
+ * flamingo_lm.py:63-65 -- SURVEY.md section 8f rank 1).  head_dim 64 or 128.  Same TMA + tcgen05 implementation
+ * (and the same mma.sync path for other layouts) as ofk_attn_fwd / ofk_attn_bwd.
  *   S = scale * Q K^T + slopes[h] * key_index  (ALiBi; slopes NULL = no bias)
  *   masked (mask[b, q, k] != 0, mask: [batch, nq, nk] bytes or NULL; and/or causal: key > query + nk - nq)
  *   scores take "finfo.min" exactly like masked_fill: a fully masked row attends uniformly.
@@ -152,7 +163,7 @@ int ofk_attn_bwd(const void* q, const void* k, const void* v, const void* o, con
  *   attention_mask): the kernel then ignores `mask`, applies the causal rule and skips key tiles above the
  *   diagonal -- a device-side decision, so no host synchronisation is needed to pick the fast path.
  *   lse: [batch, heads, nq] f32, log2 domain (consumed only by ofk_attn_dense_bwd).
- * Backward is dgrad only (the LM is frozen): dq/dk/dv bf16, fully overwritten.
+ * Backward is dgrad only (the LM is frozen): dq/dk/dv bf16, fully overwritten; workspace as for ofk_attn_bwd.
  */
 int ofk_attn_dense_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int batch, int heads,
                        int head_dim, int nq, int nk, long long q_bstride, long long ldq, long long k_bstride,
@@ -165,16 +176,15 @@ int ofk_attn_dense_bwd(const void* q, const void* k, const void* v, const void* 
                        long long ldk, long long v_bstride, long long ldv, long long o_bstride, long long ldo,
                        long long dq_bstride, long long lddq, long long dk_bstride, long long lddk,
                        long long dv_bstride, long long lddv, float scale, int causal, const unsigned char* mask,
-                       const float* slopes, const int* pure_causal_flag, void* stream);
+                       const float* slopes, const int* pure_causal_flag, void* workspace, long long workspace_bytes,
+                       void* stream);
 
-/* EXPERIMENTAL: ofk_attn_fwd on the tcgen05 tensor cores (TMA-staged Q/K/V tiles, S and O_j in TMEM, P through
- * swizzled shared memory) -- same arguments, semantics and outputs as ofk_attn_fwd; additionally requires
- * batch strides == rows * row stride.  Not validated on hardware yet and not used by any default path
- * (ops.attn_fwd selects it only with OFK_ATTN_TC=1). */
-int ofk_attn_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse, int batch, int heads, int nq,
-                    int nk, long long q_bstride, long long ldq, long long k_bstride, long long ldk, long long v_bstride,
-                    long long ldv, long long o_bstride, long long ldo, float scale, int mask_mode,
-                    const int* text_time, int keys_per_media, void* stream);
+/* Attention implementation switch, for A/B measurements and for the parity tests that compare the two paths:
+ * nonzero = always use the mma.sync kernels; 0 = tensor-core path whenever the layout allows (the default, unless
+ * the environment variable OFK_ATTN_LEGACY=1 is set when the library is loaded).  Returns the previous setting.
+ * ofk_attn_tc_launch_count(): how many tcgen05 attention kernels (forward or backward) have been launched. */
+int ofk_attn_force_legacy(int on);
+long long ofk_attn_tc_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Small fused elementwise / reduction kernels.

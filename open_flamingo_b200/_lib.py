@@ -56,18 +56,18 @@ _SIGNATURES = {
     "ofk_attn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                              c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_float, c_int, c_void_p, c_int,
                              c_void_p]),
-    "ofk_attn_fwd_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
-                                c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_float, c_int, c_void_p, c_int,
-                                c_void_p]),
+    "ofk_attn_bwd_workspace_bytes": (c_ll, [c_int, c_int, c_int, c_int, c_int]),
     "ofk_attn_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                              c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll,
-                             c_float, c_int, c_void_p, c_int, c_void_p]),
+                             c_float, c_int, c_void_p, c_int, c_void_p, c_ll, c_void_p]),
     "ofk_attn_dense_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                    c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_float, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p]),
     "ofk_attn_dense_bwd": (c_int, [c_void_p] * 10 + [c_int] * 5 + [c_ll] * 14 + [c_float, c_int, c_void_p, c_void_p,
-                                                                              c_void_p, c_void_p]),
+                                                                              c_void_p, c_void_p, c_ll, c_void_p]),
+    "ofk_attn_force_legacy": (c_int, [c_int]),
+    "ofk_attn_tc_launch_count": (c_ll, []),
     "ofk_text_time": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "ofk_cast_f32_bf16": (c_int, [c_void_p, c_void_p, c_ll, c_void_p]),
     "ofk_gate_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
@@ -104,7 +104,7 @@ def lib():
             fn = getattr(L, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if L.ofk_abi_version() != 1:
+        if L.ofk_abi_version() != 2:
             raise RuntimeError("libofk.so ABI version mismatch")
         _lib = L
     return _lib

@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "attention_tc.h"
 #include "ofk_internal.h"
 #include "ofk_ptx.cuh"
 
@@ -319,11 +320,12 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const AttnParams 
     if (row_b < p.nq) *reinterpret_cast<uint32_t*>(op + (long long)row_b * p.ldo + col) = pack_bf16x2(o[i][2] * inv_b, o[i][3] * inv_b);
   }
   if (p.lse != nullptr && t == 0) {
-    // natural-log LSE of the scaled scores; rows with no mass get +inf-safe sentinel 0 (P recomputes to 0 there
-    // because every score is -inf).
+    // log2-domain LSE of the scaled scores (same convention as the tcgen05 kernels of attention_tc.cu, so either
+    // backward can consume either forward); rows with no mass get the sentinel 0 (P recomputes to 0 there because
+    // every score is -inf).
     float* lp = p.lse + ((long long)b * p.heads + h) * p.nq;
-    if (row_a < p.nq) lp[row_a] = l_a > 0.f ? (m_a + log2f(l_a)) / LOG2E : 0.f;
-    if (row_b < p.nq) lp[row_b] = l_b > 0.f ? (m_b + log2f(l_b)) / LOG2E : 0.f;
+    if (row_a < p.nq) lp[row_a] = l_a > 0.f ? m_a + log2f(l_a) : 0.f;
+    if (row_b < p.nq) lp[row_b] = l_b > 0.f ? m_b + log2f(l_b) : 0.f;
   }
 }
 
@@ -352,7 +354,7 @@ __device__ __forceinline__ void recompute_p(const AttnParams& p, float (&s)[8][4
   // exp(scale*s - lse) == exp2(scale*log2e*s - lse*log2e)
   const float sl2 = p.scale * LOG2E;
   const float za = ra.kind == 2 ? 0.f : sl2, zb = rb.kind == 2 ? 0.f : sl2;
-  const float la = lse_a * LOG2E, lb = lse_b * LOG2E;
+  const float la = lse_a, lb = lse_b;   // LSE is stored in the log2 domain
   if (p.mask_mode == 0 && key0 + BKV <= p.nk) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -552,7 +554,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const AttnPar
         RowInfo r; r.tt = s_tt[buf][qc]; r.kind = s_kind[buf][qc];
         const bool ok = ((e & 2) ? inb_kb : inb_ka) && media_allowed(p, r, (e & 2) ? media_kb : media_ka);
         const float z = r.kind == 2 ? 0.f : sl2;
-        const float pv = ok ? ex2_approx(fmaf(st[i][e], z, -s_lse[buf][qc] * LOG2E)) : 0.f;
+        const float pv = ok ? ex2_approx(fmaf(st[i][e], z, -s_lse[buf][qc])) : 0.f;
         st[i][e] = pv;                                                                      // P^T
         dst[i][e] = pv * (dpt[i][e] - s_del[buf][qc]) * (r.kind == 2 ? 0.f : p.scale);     // dS^T
       }
@@ -609,6 +611,15 @@ extern "C" int ofk_attn_fwd(const void* q, const void* k, const void* v, void* o
   p.o_bs = o_bstride; p.ldo = ldo; p.scale = scale; p.mask_mode = mask_mode; p.kpm = keys_per_media;
   if (!q || !k || !v || !o) return ofk_set_error(OFK_ERR_ARG, "attention: null pointer");
   if (int rc = check_common(p)) return rc;
+  {
+    // default path: TMA + tcgen05 (attention_tc.cu); the mma.sync kernel below serves layouts TMA cannot describe
+    tc::Args a{};
+    a.q = q; a.k = k; a.v = v; a.out = o; a.lse = lse; a.batch = batch; a.heads = heads; a.hd = HD; a.nq = nq; a.nk = nk;
+    a.q_bs = q_bstride; a.ldq = ldq; a.k_bs = k_bstride; a.ldk = ldk; a.v_bs = v_bstride; a.ldv = ldv; a.o_bs = o_bstride;
+    a.ldo = ldo; a.scale = scale; a.dense = 0; a.mask_mode = mask_mode; a.text_time = text_time; a.kpm = keys_per_media;
+    a.stream = stream_;
+    if (tc::fwd_supported(a)) return tc::fwd(a);
+  }
   dim3 grid((nq + BQ - 1) / BQ, heads, batch);
   attn_fwd_kernel<<<grid, ATT_THREADS, 0, (cudaStream_t)stream_>>>(p);
   OFK_CHECK_LAUNCH();
@@ -621,7 +632,7 @@ extern "C" int ofk_attn_bwd(const void* q, const void* k, const void* v, const v
                             long long v_bstride, long long ldv, long long o_bstride, long long ldo,
                             long long dq_bstride, long long lddq, long long dk_bstride, long long lddk,
                             long long dv_bstride, long long lddv, float scale, int mask_mode, const int* text_time,
-                            int keys_per_media, void* stream_) {
+                            int keys_per_media, void* workspace, long long workspace_bytes, void* stream_) {
   using namespace ofk;
   AttnParams p{};
   p.q = (const __nv_bfloat16*)q; p.k = (const __nv_bfloat16*)k; p.v = (const __nv_bfloat16*)v;
@@ -635,6 +646,16 @@ extern "C" int ofk_attn_bwd(const void* q, const void* k, const void* v, const v
     return ofk_set_error(OFK_ERR_ARG, "attention bwd: null pointer");
   if (int rc = check_common(p)) return rc;
   if ((lddq | lddk | lddv) % 2 != 0) return ofk_set_error(OFK_ERR_ALIGN, "attention bwd: grad strides must be even");
+  {
+    tc::Args a{};
+    a.q = q; a.k = k; a.v = v; a.o = o; a.d_o = d_o; a.lse = const_cast<float*>(lse); a.delta = delta; a.dq = dq; a.dk = dk;
+    a.dv = dv; a.batch = batch; a.heads = heads; a.hd = HD; a.nq = nq; a.nk = nk;
+    a.q_bs = q_bstride; a.ldq = ldq; a.k_bs = k_bstride; a.ldk = ldk; a.v_bs = v_bstride; a.ldv = ldv; a.o_bs = o_bstride;
+    a.ldo = ldo; a.dq_bs = dq_bstride; a.lddq = lddq; a.dk_bs = dk_bstride; a.lddk = lddk; a.dv_bs = dv_bstride; a.lddv = lddv;
+    a.scale = scale; a.dense = 0; a.mask_mode = mask_mode; a.text_time = text_time; a.kpm = keys_per_media;
+    a.workspace = workspace; a.workspace_bytes = workspace_bytes; a.stream = stream_;
+    if (tc::bwd_supported(a)) return tc::bwd(a);
+  }
   cudaStream_t stream = (cudaStream_t)stream_;
   const long long rows = (long long)batch * heads * nq;
   attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(p);

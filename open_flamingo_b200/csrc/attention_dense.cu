@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "attention_tc.h"
 #include "ofk_internal.h"
 #include "ofk_ptx.cuh"
 
@@ -562,6 +563,14 @@ extern "C" int ofk_attn_dense_fwd(const void* q, const void* k, const void* v, v
   p.scale = scale;
   if (!q || !k || !v || !o) return ofk_set_error(OFK_ERR_ARG, "dense attention: null pointer");
   if (int rc = validate(p, head_dim)) return rc;
+  {
+    ofk::tc::Args a{};
+    a.q = q; a.k = k; a.v = v; a.out = o; a.lse = lse; a.batch = batch; a.heads = heads; a.hd = head_dim; a.nq = nq; a.nk = nk;
+    a.q_bs = q_bstride; a.ldq = ldq; a.k_bs = k_bstride; a.ldk = ldk; a.v_bs = v_bstride; a.ldv = ldv; a.o_bs = o_bstride;
+    a.ldo = ldo; a.scale = scale; a.dense = 1; a.causal = causal; a.mask = mask; a.slopes = slopes; a.pure_causal = pure_causal_flag;
+    a.stream = stream;
+    if (ofk::tc::fwd_supported(a)) return ofk::tc::fwd(a);
+  }
   return head_dim == 64 ? launch_fwd<64>(p, (cudaStream_t)stream) : launch_fwd<128>(p, (cudaStream_t)stream);
 }
 
@@ -571,7 +580,8 @@ extern "C" int ofk_attn_dense_bwd(const void* q, const void* k, const void* v, c
                                   long long ldk, long long v_bstride, long long ldv, long long o_bstride, long long ldo,
                                   long long dq_bstride, long long lddq, long long dk_bstride, long long lddk,
                                   long long dv_bstride, long long lddv, float scale, int causal, const unsigned char* mask,
-                                  const float* slopes, const int* pure_causal_flag, void* stream) {
+                                  const float* slopes, const int* pure_causal_flag, void* workspace,
+                                  long long workspace_bytes, void* stream) {
   using namespace ofk::dense;
   Params p{};
   p.q = (const __nv_bfloat16*)q; p.k = (const __nv_bfloat16*)k; p.v = (const __nv_bfloat16*)v; p.o = (const __nv_bfloat16*)o;
@@ -582,5 +592,15 @@ extern "C" int ofk_attn_dense_bwd(const void* q, const void* k, const void* v, c
   p.dq_bs = dq_bstride; p.lddq = lddq; p.dk_bs = dk_bstride; p.lddk = lddk; p.dv_bs = dv_bstride; p.lddv = lddv; p.scale = scale;
   if (!q || !k || !v || !o || !d_o || !lse || !delta || !dq || !dk || !dv) return ofk_set_error(OFK_ERR_ARG, "dense attention bwd: null pointer");
   if (int rc = validate(p, head_dim)) return rc;
+  {
+    ofk::tc::Args a{};
+    a.q = q; a.k = k; a.v = v; a.o = o; a.d_o = d_o; a.lse = const_cast<float*>(lse); a.delta = delta; a.dq = dq; a.dk = dk;
+    a.dv = dv; a.batch = batch; a.heads = heads; a.hd = head_dim; a.nq = nq; a.nk = nk;
+    a.q_bs = q_bstride; a.ldq = ldq; a.k_bs = k_bstride; a.ldk = ldk; a.v_bs = v_bstride; a.ldv = ldv; a.o_bs = o_bstride;
+    a.ldo = ldo; a.dq_bs = dq_bstride; a.lddq = lddq; a.dk_bs = dk_bstride; a.lddk = lddk; a.dv_bs = dv_bstride; a.lddv = lddv;
+    a.scale = scale; a.dense = 1; a.causal = causal; a.mask = mask; a.slopes = slopes; a.pure_causal = pure_causal_flag;
+    a.workspace = workspace; a.workspace_bytes = workspace_bytes; a.stream = stream;
+    if (ofk::tc::bwd_supported(a)) return ofk::tc::bwd(a);
+  }
   return head_dim == 64 ? launch_bwd<64>(p, (cudaStream_t)stream) : launch_bwd<128>(p, (cudaStream_t)stream);
 }

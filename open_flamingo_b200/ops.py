@@ -149,7 +149,29 @@ def _bstride_ld(t, name):
     return t.stride(0), t.stride(1)
 
 
-_ATTN_TC = os.environ.get("OFK_ATTN_TC", "0") == "1"
+def attn_force_legacy(on):
+    """A/B switch: True = always the mma.sync attention kernels, False = TMA + tcgen05 whenever the layout allows
+    (the default).  Returns the previous setting."""
+    return bool(L.lib().ofk_attn_force_legacy(int(bool(on))))
+
+
+def attn_tc_launch_count():
+    return int(L.lib().ofk_attn_tc_launch_count())
+
+
+_attn_ws = {}
+
+
+def _attn_workspace(device, nbytes):
+    """fp32 dQ accumulator of the tensor-core attention backward (one per (device, stream), grown on demand)."""
+    if nbytes <= 0:
+        return None
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _attn_ws.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes), device=device, dtype=torch.uint8)
+        _attn_ws[key] = ws
+    return ws
 
 
 def attn_fwd(q, k, v, heads, scale, *, mask_mode=L.MASK_NONE, text_time=None, keys_per_media=64, out=None,
@@ -171,14 +193,9 @@ def attn_fwd(q, k, v, heads, scale, *, mask_mode=L.MASK_NONE, text_time=None, ke
         if text_time is None or text_time.dtype != torch.int32 or tuple(text_time.shape) != (B, nq):
             raise ValueError("media mask needs int32 text_time of shape [B, nq]")
         text_time = text_time.contiguous()
-    # OFK_ATTN_TC=1 selects the EXPERIMENTAL tcgen05 forward core (attention_tc.cu; not validated on hardware yet)
-    # for the layouts it supports; every default path uses the mma.sync kernel of attention.cu.
-    fn = L.lib().ofk_attn_fwd
-    if _ATTN_TC and qb == nq * ldq and kb == nk * ldk and vb == nk * ldv and ldo % 8 == 0 and ob % 8 == 0 and \
-            (mask_mode == L.MASK_NONE or (keys_per_media % 16 == 0 and nk % keys_per_media == 0)):
-        fn = L.lib().ofk_attn_fwd_tc
-    L.check(fn(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), L.ptr(lse), B, heads, nq, nk,
-               qb, ldq, kb, ldk, vb, ldv, ob, ldo, scale, mask_mode, L.ptr(text_time), keys_per_media, L.stream_ptr()))
+    L.check(L.lib().ofk_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), L.ptr(lse), B, heads, nq, nk,
+                                 qb, ldq, kb, ldk, vb, ldv, ob, ldo, scale, mask_mode, L.ptr(text_time), keys_per_media,
+                                 L.stream_ptr()))
     return out, lse
 
 
@@ -206,10 +223,12 @@ def attn_bwd(q, k, v, o, d_o, lse, heads, scale, *, mask_mode=L.MASK_NONE, text_
     dvb, lddv = _bstride_ld(dv, "dv")
     if text_time is not None:
         text_time = text_time.contiguous()
+    ws = _attn_workspace(q.device, L.lib().ofk_attn_bwd_workspace_bytes(B, heads, 64, nq, nk))
     L.check(L.lib().ofk_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), d_o.data_ptr(), lse.data_ptr(),
                                  delta.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, heads, nq, nk,
                                  qb, ldq, kb, ldk, vb, ldv, ob, ldo, dqb, lddq, dkb, lddk, dvb, lddv, scale, mask_mode,
-                                 L.ptr(text_time), keys_per_media, L.stream_ptr()))
+                                 L.ptr(text_time), keys_per_media, L.ptr(ws), 0 if ws is None else ws.numel(),
+                                 L.stream_ptr()))
     return dq, dk, dv
 
 
@@ -351,11 +370,13 @@ def attn_dense_bwd(q, k, v, o, d_o, lse, heads, head_dim, scale, *, causal=False
     dqb, lddq = _bstride_ld(dq, "dq")
     dkb, lddk = _bstride_ld(dk, "dk")
     dvb, lddv = _bstride_ld(dv, "dv")
+    ws = _attn_workspace(q.device, L.lib().ofk_attn_bwd_workspace_bytes(B, heads, head_dim, nq, nk))
     L.check(L.lib().ofk_attn_dense_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), d_o.data_ptr(),
                                        lse.data_ptr(), delta.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
                                        B, heads, head_dim, nq, nk, qb, ldq, kb, ldk, vb, ldv, ob, ldo, dqb, lddq, dkb,
                                        lddk, dvb, lddv, scale, int(causal), L.ptr(mask), L.ptr(slopes),
-                                       L.ptr(pure_causal_flag), L.stream_ptr()))
+                                       L.ptr(pure_causal_flag), L.ptr(ws), 0 if ws is None else ws.numel(),
+                                       L.stream_ptr()))
     return dq, dk, dv
 
 

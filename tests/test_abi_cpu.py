@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in ofk.h but not exported by libofk.so"
     assert sorted(_lib.exported_symbols()) == declared, "ctypes signature table and ofk.h disagree"
     loaded = _lib.lib()
-    assert loaded.ofk_abi_version() == 1
+    assert loaded.ofk_abi_version() == 2
     assert isinstance(_lib.launch_count(), int)
 
 
