@@ -53,6 +53,11 @@ def parse_args():
                     help="frozen-LM decoder blocks: 'fused' = libofk kernels (lm_blocks.py), 'eager' = HF PyTorch "
                          "modules as in the reference")
     ap.add_argument("--cpu-sample-batch", type=int, default=1)
+    ap.add_argument("--no-gpu-eager-ref", action="store_true",
+                    help="skip timing the reference's eager-PyTorch path (oracle restatement) on the same GPU")
+    ap.add_argument("--micro-batches", type=int, default=1,
+                    help="backward passes per optimizer step (the reference's step is LAION + MMC4 = 2, "
+                         "train_utils.py:118,172); all but the last run under trainer.no_sync(); tokens/s counts all of them")
     return ap.parse_args()
 
 
@@ -261,6 +266,38 @@ def time_cpu_oracle(model_name, sample_batch, t_img, t_txt, steps, warmup):
                        f"fp32, torch.set_num_threads({cores}), {dt*1e3:.0f} ms/step"), dt
 
 
+def time_gpu_eager_reference(model, every, batch, steps):
+    """The like-for-like bar: the reference's eager-PyTorch forward + backward -- the oracle
+    restatement, module for module the reference's ops (oracle/flamingo_oracle.py, pinned to the unmodified reference by
+    tests/golden) around the same HF LM -- on THIS GPU, same weights, same batch, fp32 and torch.autocast(bf16)
+    (train_utils.py:34-43).  No optimizer / clip in its timed region (ours includes them), so the ratio is conservative."""
+    from oracle.harness import oracle_from_model, oracle_train_step
+    out = {}
+    orc, sd, trainable = oracle_from_model(model, every)
+    tokens = batch["lang_x"].numel()
+    for name, dt in (("amp_bf16", torch.bfloat16), ("fp32", None)):
+        try:
+            for _ in range(2):
+                oracle_train_step(orc, sd, trainable, batch, amp_dtype=dt)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                oracle_train_step(orc, sd, trainable, batch, amp_dtype=dt)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"value": tokens / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms}
+        except Exception as e:  # pragma: no cover - e.g. out of memory on a smaller part
+            out[name] = {"error": repr(e)[:200]}
+            torch.cuda.empty_cache()
+    out["what"] = ("reference eager PyTorch path (oracle restatement of open_flamingo/src on the same HF LM), fwd+bwd only, "
+                   f"same GPU / weights / batch, {steps} steps after 2 warm-up")
+    del orc, sd
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -306,17 +343,34 @@ def run_ours(args):
     B, T_img, T_txt = args.batch, args.t_img, args.t_txt
     host = synthetic_batch(B, T_img, T_txt, media_id, eoc_id, mpt_kw["vocab_size"], image_size=vit_cfg["image_size"],
                            seed=100 + rank, pin=True)
-    resident = {k: v.to(dev) for k, v in host.items()}
-    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    MB = max(1, args.micro_batches)
+    hosts = [host] + [synthetic_batch(B, T_img, T_txt, media_id, eoc_id, mpt_kw["vocab_size"], image_size=vit_cfg["image_size"],
+                                      seed=1000 * (i + 1) + rank, pin=True) for i in range(MB - 1)]
+    residents = [{k: v.to(dev) for k, v in hb.items()} for hb in hosts]
+    resident = residents[0] if MB == 1 else residents
+    host = hosts[0] if MB == 1 else hosts
+    h2d_bytes = sum(v.numel() * v.element_size() for hb in hosts for v in hb.values())
 
-    def train_step(batch):
-        trainer.zero_grad()
+    def fwd_bwd(batch):
         with torch.autocast("cuda", dtype=torch.bfloat16):
             out = model(vision_x=batch["vision_x"], lang_x=batch["lang_x"], attention_mask=batch["attention_mask"],
                         labels=batch["labels"])
         out.loss.backward()
-        trainer.step()
         return out.loss
+
+    def train_step(batch):
+        batches = batch if isinstance(batch, (list, tuple)) else [batch]
+        trainer.zero_grad()
+        loss = None
+        for i, b_ in enumerate(batches):
+            if i + 1 < len(batches):
+                with trainer.no_sync():     # gradient accumulation: chunks are reduced during the LAST backward only
+                    l_ = fwd_bwd(b_)
+            else:
+                l_ = fwd_bwd(b_)
+            loss = l_ if loss is None else loss + l_
+        trainer.step()
+        return loss
 
     def barrier():
         if world > 1:
@@ -367,7 +421,7 @@ def run_ours(args):
     ms_total = timed(lambda: run_step(resident), args.steps)
     clocks = sampler.stop() if rank == 0 else {}
     ms_step = ms_total / args.steps
-    tokens = world * B * T_txt
+    tokens = world * B * T_txt * MB
     # host time needed to ENQUEUE one step (no sync inside): must stay well below ms_step or the GPU starves
     torch.cuda.synchronize()
     t_cpu0 = time.perf_counter()
@@ -390,7 +444,8 @@ def run_ours(args):
         if graphed is not None:
             loss = graphed(host)                 # pinned host tensors -> static device buffers (async H2D) -> replay
         else:
-            loss = train_step({k: v.to(dev, non_blocking=True) for k, v in host.items()})
+            hb = host if isinstance(host, list) else [host]
+            loss = train_step([{k: v.to(dev, non_blocking=True) for k, v in h_.items()} for h_ in hb])
         return float(loss.item())
 
     for _ in range(2):
@@ -416,11 +471,24 @@ def run_ours(args):
         roofline = {"bound": "tensor", "kernel": "ofk::gemm2_kernel<A_MN,B_MN,EPI> / gemm_kernel<BN,...> (tcgen05 cta_group::2 / ::1, every launch in the timed region)",
                     "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                     "peak_source": peak_src, "traffic": traffic,
+                    "traffic_source": "STATIC: mean dram__bytes_read+write per launch of the FFN GEMMs in the committed ncu --set full "
+                                      "capture profiles/gemm_traffic.json (see its `build` field), not re-measured by this run",
                     "launches_per_step": gemm_n / args.steps, "gemm_ms_per_step": gemm_ms / args.steps,
                     "share_of_step": gemm_ms / ms_instr if ms_instr else None,
                     "instrumented_ms_per_step": ms_instr / args.steps,
                     "by_variant": {k: {"TFLOP/s": v[1] / (v[0] * 1e-3) / 1e12 if v[0] else 0.0, "ms_per_step": v[0] / args.steps,
                                        "launches_per_step": v[2] / args.steps} for k, v in sorted(gemm_by.items())}}
+        gpu_eager = None
+        if not args.no_gpu_eager_ref and world == 1:
+            try:
+                graphed = None                  # release the captured graph's private pool before the eager run
+                torch.cuda.empty_cache()
+                gpu_eager = time_gpu_eager_reference(model, every, residents[0], steps=3)
+                for k_ in ("amp_bf16", "fp32"):
+                    if "value" in gpu_eager.get(k_, {}):
+                        gpu_eager[k_]["ours_over_this"] = (tokens / (ms_step * 1e-3)) / gpu_eager[k_]["value"]
+            except Exception as e:  # pragma: no cover
+                gpu_eager = {"error": repr(e)[:200]}
         cpu_baseline = None
         if not args.no_cpu_baseline and world == 1:
             try:
@@ -432,7 +500,7 @@ def run_ours(args):
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": f"{args.model.upper()} (ViT-L/14 + {LM_NAME.get(args.model, 'tiny')}-shaped HF MptForCausalLM, xattn_every={every}) "
                                        "amp_bf16 train step: fwd+bwd+grad all-reduce+clip+AdamW",
-                           "global_batch": world * B, "per_gpu_batch": B, "t_img": T_img, "seq_len": T_txt,
+                           "global_batch": world * B * MB, "per_gpu_batch": B, "micro_batches": MB, "t_img": T_img, "seq_len": T_txt,
                            "parallelism": f"dp{world}", "frozen_lm_blocks": args.lm, "cuda_graph": graphed is not None, "l2": "per-step working set (>10 GB weights+activations) exceeds the 126 MB L2; no explicit flush",
                            "trainable_params": sum(p.numel() for p in model.parameters() if p.requires_grad)},
                 "e2e": {"value": tokens / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
@@ -441,6 +509,8 @@ def run_ours(args):
                 "roofline": roofline}
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
+        if gpu_eager is not None:
+            line["gpu_eager_reference"] = gpu_eager
         print(json.dumps(line), flush=True)
     if world > 1:
         # Tear down in a hang-proof order: release the captured graph (it holds NCCL kernels) before touching the

@@ -82,6 +82,12 @@ int ofk_gemm_bf16_ws(int epi, int a_mn_major, int b_mn_major, const void* A, lon
                      void* out2, long long ldo2, const void* aux, long long ldaux, const float* bias,
                      const float* gate, void* workspace, long long workspace_bytes, void* stream);
 
+/* Leave `n` SMs (rounded down to whole pairs, at most 64) out of every persistent GEMM grid launched from now on; returns
+ * the previous value.  The data-parallel step uses it while gradient-chunk all-reduces are in flight (train.GradBucket):
+ * a persistent grid that owns all 148 SMs lets NCCL's CTAs in only at kernel boundaries, which serialises the
+ * "overlapped" reduction behind each GEMM.  0 restores the full grid. */
+int ofk_gemm_reserve_sms(int n);
+
 /* Same GEMM with grouped row maps (logical row r -> (r / rows_per_group) * group_stride + group_offset + r % rpg):
  *   out_*  : where the rows of `out` go inside a larger interleaved buffer (STORE_BF16 / BIAS_BF16 / STORE_F32);
  *   a_k_*  : which physical rows of an MN-major A form the reduction dimension (rows_per_group % 64 == 0).

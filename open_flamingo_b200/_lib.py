@@ -41,6 +41,7 @@ _SIGNATURES = {
                               c_void_p]),
     "ofk_make_labels": (c_int, [c_void_p, c_ll, c_int, c_int, c_ll, c_ll, c_ll, c_int, c_void_p, c_ll, c_void_p]),
     "ofk_gemm_workspace_bytes": (c_ll, []),
+    "ofk_gemm_reserve_sms": (c_int, [c_int]),
     "ofk_gemm_bf16_ws": (c_int, [c_int, c_int, c_int, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int,
                                  c_int, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p,
                                  c_void_p, c_ll, c_void_p]),

@@ -448,6 +448,293 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
   }
 }
 
+// ================================================================================================ forward, pipelined
+// Second-generation forward: 64-key tiles for both head dims, the S accumulator double-buffered in TMEM (S_{j+1} = Q K_{j+1}^T
+// is issued while the softmax warps work on S_j), a two-stage K ring, the scores of a tile held in registers (one TMEM
+// read, one pass), and FA4-style lazy rescaling: the running output in TMEM is only rescaled when some row's maximum
+// grew by more than 2^8 since the value the accumulators are expressed in (p <= 256 is harmless in fp32 / bf16), so
+// most tiles skip the TMEM read-modify-write and the exponentials of tile j overlap P V_{j-1}.
+template <int HD>
+struct Fwd2Cfg {
+  static constexpr int BKT = 64;
+  static constexpr int ATOMS = HD / 64;
+  static constexpr int Q_ATOM = 128 * 128;
+  static constexpr int KV_ATOM = BKT * 128;            // 8 KiB: 64 keys x 64 head-dim columns
+  static constexpr int Q_BYTES = ATOMS * Q_ATOM;
+  static constexpr int KV_BYTES = ATOMS * KV_ATOM;
+  static constexpr int NKST = 2;
+  static constexpr int NVST = HD == 64 ? 2 : 1;        // shared memory: 64 KiB (hd 64) / 96 KiB (hd 128) -> 2 CTAs / SM
+  static constexpr int P_BYTES = Q_ATOM;               // [128 queries x 64 keys] bf16, one swizzle atom
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = OFF_Q + Q_BYTES;
+  static constexpr int OFF_V = OFF_K + NKST * KV_BYTES;
+  static constexpr int OFF_P = OFF_V + NVST * KV_BYTES;
+  static constexpr int OFF_BAR = OFF_P + P_BYTES;
+  static constexpr int SMEM = OFF_BAR + 256 + 1024;
+  static constexpr uint32_t TMEM_COLS = 256;           // S[0]: 0..63, S[1]: 64..127, O: 128..128+HD
+  static constexpr uint32_t O_COL = 128;
+};
+constexpr float RESCALE_THRESHOLD = 8.0f;              // log2 units
+
+template <int HD, bool DENSE>
+__global__ void __launch_bounds__(FWD_THREADS, 2)
+attn_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                    const __grid_constant__ CUtensorMap tma_v, const Params p) {
+  using C = Fwd2Cfg<HD>;
+  constexpr int BKT = C::BKT;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + C::OFF_Q;
+  uint8_t* sK = smem + C::OFF_K;
+  uint8_t* sV = smem + C::OFF_V;
+  uint8_t* sP = smem + C::OFF_P;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;     // [2]
+  uint64_t* v_full = bars + 3;     // [NVST]
+  uint64_t* v_empty = bars + 5;    // [NVST]
+  uint64_t* s_full = bars + 7;     // [2]
+  uint64_t* p_full = bars + 9;
+  uint64_t* o_full = bars + 10;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+  int* s_range = reinterpret_cast<int*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+
+  if (threadIdx.x == 0) { s_range[0] = 1 << 30; s_range[1] = -1; s_range[2] = 0; }
+  if (warp == 5 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&k_full[i], 1); mbar_init(&s_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+    mbar_init(p_full, 128); mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    if (lane == 0) { tma_prefetch_desc(&tma_q); tma_prefetch_desc(&tma_k); tma_prefetch_desc(&tma_v); }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  __syncthreads();
+
+  bool causal = false;
+  const unsigned char* mask = nullptr;
+  if constexpr (DENSE) {
+    causal = p.causal != 0; mask = p.mask;
+    if (p.pure_causal != nullptr && *p.pure_causal != 0) { mask = nullptr; causal = true; }
+  }
+  RowCtx<DENSE> rc;
+  if constexpr (!DENSE) {
+    rc.kind = 1; rc.tt = 0; rc.z = 0.f;
+    if (warp < 4) {
+      const MediaRow r = classify(p, b, q0 + threadIdx.x);
+      rc.kind = r.kind; rc.tt = r.tt;
+      rc.z = r.kind == 2 ? 0.f : p.scale * LOG2E;
+      if (p.mask_mode != 0) {
+        if (r.kind == 0) { atomicMin(&s_range[0], r.tt); atomicMax(&s_range[1], r.tt); }
+        if (r.kind == 2) s_range[2] = 1;
+      }
+    }
+  } else {
+    const int row = q0 + (int)threadIdx.x;
+    rc.valid = warp < 4 && row < p.nq;
+    rc.causal_last = causal ? row + (p.nk - p.nq) : 0x7fffffff;
+    rc.mrow = (mask != nullptr && rc.valid) ? mask + ((long long)b * p.nq + row) * p.nk : nullptr;
+    rc.sl2 = p.scale * LOG2E;
+    rc.slope2 = p.slopes != nullptr ? p.slopes[h] * LOG2E : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  int lo = 0, hi = p.nk;
+  if constexpr (!DENSE) {
+    if (p.mask_mode != 0 && s_range[2] == 0) {
+      if (s_range[1] < 0) { lo = 0; hi = 0; }
+      else {
+        hi = min(p.nk, s_range[1] * p.kpm);
+        lo = p.mask_mode == 1 ? max(0, (s_range[0] - 1) * p.kpm) : 0;
+      }
+    }
+  } else {
+    if (causal && mask == nullptr) hi = max(0, min(p.nk, min(q0 + 127, p.nq - 1) + (p.nk - p.nq) + 1));
+  }
+  const int t_lo = lo / BKT, t_hi = (hi + BKT - 1) / BKT;
+  const int nsteps = max(0, t_hi - t_lo);
+
+  if (warp == 4) {
+    // ===================== TMA producer =====================
+    if (lane == 0 && nsteps > 0) {
+      mbar_arrive_expect_tx(q_full, C::Q_BYTES);
+#pragma unroll
+      for (int a = 0; a < C::ATOMS; ++a) tma_load_2d(sQ + a * C::Q_ATOM, &tma_q, q_full, h * HD + 64 * a, b * p.nq + q0);
+      for (int it = 0; it < nsteps; ++it) {
+        const int key0 = (t_lo + it) * BKT;
+        const int kb = it & 1;
+        if (it >= 2) mbar_wait(&s_full[kb], ((it - 2) >> 1) & 1);        // S_{it-2} retired: K stage kb is free
+        mbar_arrive_expect_tx(&k_full[kb], C::KV_BYTES);
+#pragma unroll
+        for (int a = 0; a < C::ATOMS; ++a)
+          tma_load_2d(sK + kb * C::KV_BYTES + a * C::KV_ATOM, &tma_k, &k_full[kb], h * HD + 64 * a, b * p.nk + key0);
+        const int vb = it % C::NVST;
+        if (it >= C::NVST) mbar_wait(&v_empty[vb], ((it - C::NVST) / C::NVST) & 1);   // P V_{it-NVST} retired
+        mbar_arrive_expect_tx(&v_full[vb], C::KV_BYTES);
+#pragma unroll
+        for (int a = 0; a < C::ATOMS; ++a)
+          tma_load_2d(sV + vb * C::KV_BYTES + a * C::KV_ATOM, &tma_v, &v_full[vb], h * HD + 64 * a, b * p.nk + key0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    if (lane == 0 && nsteps > 0) {
+      const uint32_t aq = smem_u32(sQ), ak = smem_u32(sK), av = smem_u32(sV), ap = smem_u32(sP);
+      auto issue_s = [&](int it) {                                  // S_it -> TMEM buffer it & 1, K stage it & 1
+        const int key0 = (t_lo + it) * BKT;
+        const int n_eff = min(BKT, ((p.nk - key0) + 15) & ~15);
+        const uint32_t idesc = make_idesc_bf16(128, n_eff, 0, 0);
+        const uint32_t kb = ak + (it & 1) * C::KV_BYTES;
+        mbar_wait(&k_full[it & 1], (it >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk)
+          umma_bf16(tmem_base + (it & 1) * BKT, make_smem_desc_sw128(aq + (kk >> 2) * C::Q_ATOM + (kk & 3) * 32, 0, 1024),
+                    make_smem_desc_sw128(kb + (kk >> 2) * C::KV_ATOM + (kk & 3) * 32, 0, 1024), idesc, kk > 0 ? 1u : 0u);
+        umma_commit(&s_full[it & 1]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      if (nsteps > 1) issue_s(1);
+      for (int it = 0; it < nsteps; ++it) {
+        const int key0 = (t_lo + it) * BKT;
+        const int n_eff = min(BKT, ((p.nk - key0) + 15) & ~15);
+        const int vb = it % C::NVST;
+        mbar_wait(p_full, it & 1);                                  // P_it in smem, S_it consumed, O rescaled
+        mbar_wait(&v_full[vb], (it / C::NVST) & 1);
+        tc_fence_after();
+        constexpr uint32_t idesc_o = make_idesc_bf16(128, HD, 0, 1);
+        const uint32_t vbase = av + vb * C::KV_BYTES;
+        for (int ks = 0; ks < n_eff / 16; ++ks)
+          umma_bf16(tmem_base + C::O_COL, make_smem_desc_sw128(ap + ks * 32, 0, 1024),
+                    make_smem_desc_sw128(vbase + ks * 2048, C::KV_ATOM, 1024), idesc_o, (it > 0 || ks > 0) ? 1u : 0u);
+        umma_commit(o_full);
+        umma_commit(&v_empty[vb]);
+        if (it + 2 < nsteps) issue_s(it + 2);                       // S buffer / K stage it & 1 are free again
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== softmax / output (thread = query row = TMEM lane) =====================
+    const int row = q0 + (int)threadIdx.x;
+    const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    float m_used = -INFINITY, l = 0.f;          // the accumulators (O in TMEM, l) are expressed relative to m_used
+    const uint32_t p_row = smem_u32(sP) + threadIdx.x * 128;
+    const int sw = threadIdx.x & 7;
+    for (int it = 0; it < nsteps; ++it) {
+      const int key0 = (t_lo + it) * BKT;
+      const int n_eff = min(BKT, ((p.nk - key0) + 15) & ~15);
+      const uint32_t t_s = t_row + (it & 1) * BKT;
+      mbar_wait(&s_full[it & 1], (it >> 1) & 1);
+      tc_fence_after();
+      uint32_t acc[64];
+      tmem_ld16(t_s, *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));
+      if (n_eff > 16) tmem_ld16(t_s + 16, *reinterpret_cast<uint32_t(*)[16]>(&acc[16]));
+      if (n_eff > 32) tmem_ld16(t_s + 32, *reinterpret_cast<uint32_t(*)[16]>(&acc[32]));
+      if (n_eff > 48) tmem_ld16(t_s + 48, *reinterpret_cast<uint32_t(*)[16]>(&acc[48]));
+      tmem_ld_wait();
+      float s[64];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (g * 16 < n_eff) {
+          scores16<DENSE>(p, rc, &acc[g * 16], key0 + g * 16, &s[g * 16]);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, s[g * 16 + i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) s[g * 16 + i] = -INFINITY;
+        }
+      }
+      const bool grow = mx > m_used + RESCALE_THRESHOLD || (m_used == -INFINITY && mx > -INFINITY);
+      const float m_next = grow ? mx : m_used;
+      const float sub = m_next == -INFINITY ? 0.f : m_next;
+      const float corr = grow ? ex2_approx(m_used - sub) : 1.0f;     // m_used = -inf -> 0
+      float rs = 0.f;
+      uint32_t w[32];
+#pragma unroll
+      for (int i = 0; i < 64; i += 2) {
+        const float p0 = ex2_approx(s[i] - sub), p1 = ex2_approx(s[i + 1] - sub);
+        rs += p0 + p1;
+        w[i >> 1] = pack_bf16x2(p0, p1);
+      }
+      l = l * corr + rs;
+      m_used = m_next;
+      if (it > 0) {
+        mbar_wait(o_full, (it - 1) & 1);                             // P V_{it-1} retired: P buffer free, O complete
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, grow)) {
+#pragma unroll 1
+          for (int c = 0; c < HD / 32; ++c) {
+            uint32_t o32[32];
+            tmem_ld16(t_row + C::O_COL + c * 32, *reinterpret_cast<uint32_t(*)[16]>(&o32[0]));
+            tmem_ld16(t_row + C::O_COL + c * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&o32[16]));
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o32[i] = __float_as_uint(__uint_as_float(o32[i]) * corr);
+            tmem_st16(t_row + C::O_COL + c * 32, *reinterpret_cast<uint32_t(*)[16]>(&o32[0]));
+            tmem_st16(t_row + C::O_COL + c * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&o32[16]));
+          }
+          tmem_st_wait();
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j * 8 < n_eff) st_shared_v4(p_row + ((j ^ sw) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    if (nsteps > 0) {
+      mbar_wait(o_full, (nsteps - 1) & 1);
+      tc_fence_after();
+    }
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    __nv_bfloat16* op = p.out + b * p.o_bs + (long long)row * p.ldo + h * HD;
+#pragma unroll 1
+    for (int c = 0; c < HD / 32; ++c) {
+      uint32_t o32[32];
+      if (nsteps > 0) {   // block-uniform: tcgen05.ld is .sync.aligned, it must never sit under a per-row condition
+        tmem_ld16(t_row + C::O_COL + c * 32, *reinterpret_cast<uint32_t(*)[16]>(&o32[0]));
+        tmem_ld16(t_row + C::O_COL + c * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&o32[16]));
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o32[i] = 0u;
+      }
+      if (row < p.nq) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(o32[8 * j]) * inv, __uint_as_float(o32[8 * j + 1]) * inv);
+          v.y = pack_bf16x2(__uint_as_float(o32[8 * j + 2]) * inv, __uint_as_float(o32[8 * j + 3]) * inv);
+          v.z = pack_bf16x2(__uint_as_float(o32[8 * j + 4]) * inv, __uint_as_float(o32[8 * j + 5]) * inv);
+          v.w = pack_bf16x2(__uint_as_float(o32[8 * j + 6]) * inv, __uint_as_float(o32[8 * j + 7]) * inv);
+          if (!(l > 0.f)) v = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(op + c * 32 + 8 * j) = v;
+        }
+      }
+    }
+    if (row < p.nq && p.lse != nullptr) p.lse[((long long)b * p.heads + h) * p.nq + row] = l > 0.f ? m_used + log2f(l) : 0.f;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
 // ================================================================================================ backward
 // delta[b, h, q] = sum_d dO[q, d] * O[q, d]
 template <int HD>
@@ -526,8 +813,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
   uint8_t* sdST = smem + C::OFF_DST;
   float* s_lse = reinterpret_cast<float*>(smem + C::OFF_ROW);
   float* s_del = s_lse + 128;
-  int* s_tt = reinterpret_cast<int*>(s_del + 128);
-  int* s_kind = s_tt + 128;
+  int* s_meta = reinterpret_cast<int*>(s_del + 128);   // media rules: kind | text_time << 2 per query row
   int* s_qlist = reinterpret_cast<int*>(smem + C::OFF_QLIST);
   int* s_nqt = s_qlist + C::MAXQT;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
@@ -696,19 +982,20 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
     for (int idx = 0; idx < nqt; ++idx) {
       const int q0 = s_qlist[idx] * 128;
       const int n_eff = min(128, ((p.nq - q0) + 15) & ~15);
-      // ---- stage this query tile's row data (the previous tile's readers are all past b_done(idx-1))
+      // ---- stage this query tile's row data (the previous tile's readers are all past b_done(idx-1)).  Rows that
+      //      contribute nothing (outside the problem, zero rows) get lse = +inf, so exp2(s - lse) is exactly 0.
       if (tid < 128) {
         const int row = q0 + tid;
         const bool ok = row < p.nq;
         const long long ri = ((long long)b * p.heads + h) * p.nq + row;
-        s_lse[tid] = ok ? p.lse[ri] : 0.f;
-        s_del[tid] = ok ? p.delta[ri] : 0.f;
+        float lse_v = ok ? p.lse[ri] : INFINITY;
         if constexpr (!DENSE) {
           const MediaRow r = classify(p, b, row);
-          s_tt[tid] = r.tt; s_kind[tid] = r.kind;
-        } else {
-          s_kind[tid] = ok ? 0 : 1;
+          if (r.kind == 1) lse_v = INFINITY;
+          s_meta[tid] = r.kind | (r.tt << 2);
         }
+        s_lse[tid] = lse_v;
+        s_del[tid] = ok ? p.delta[ri] : 0.f;
       }
       named_bar_sync(1, 256);
       mbar_wait(a_done, idx & 1);
@@ -729,35 +1016,42 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
         tmem_ld_wait();
         uint32_t wp[16], wd[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float pv[2], dsv[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int cc = col0 + i + e;                           // query column
-            float pe = 0.f, de = 0.f;
-            if (i < 16 || two) {
-              const float lse_c = s_lse[cc], del_c = s_del[cc];
-              const int kind = s_kind[cc];
-              const float sraw = __uint_as_float(sv[i + e]), dpraw = __uint_as_float(dpv[i + e]);
-              if constexpr (!DENSE) {
-                const bool ok = key_ok && media_allowed(p.mask_mode, kind, s_tt[cc], media_k);
-                const float z = kind == 2 ? 0.f : sl2;
-                pe = ok ? ex2_approx(fmaf(sraw, z, -lse_c)) : 0.f;
-                de = kind == 2 ? 0.f : pe * (dpraw - del_c) * p.scale;
-              } else {
-                const int qrow = q0 + cc;
-                const bool valid = key_ok && kind == 0;
-                bool masked = key > qrow + off && causal;
-                if (mask != nullptr && valid && !masked) masked = mask[((long long)b * p.nq + qrow) * p.nk + key] != 0;
-                const float sc = masked ? MASKED : sraw * sl2 + slope_key;
-                pe = valid ? ex2_approx(sc - lse_c) : 0.f;
-                de = (valid && !masked) ? pe * (dpraw - del_c) * p.scale : 0.f;
-              }
+        for (int i = 0; i < 32; i += 4) {
+          float pv[4] = {0.f, 0.f, 0.f, 0.f}, dsv[4] = {0.f, 0.f, 0.f, 0.f};
+          if (i < 16 || two) {
+            const int cc = col0 + i;                               // 4 query columns: broadcast 16-byte reads of their row data
+            const float4 L4 = *reinterpret_cast<const float4*>(&s_lse[cc]);
+            const float4 D4 = *reinterpret_cast<const float4*>(&s_del[cc]);
+            const float lse4[4] = {L4.x, L4.y, L4.z, L4.w}, del4[4] = {D4.x, D4.y, D4.z, D4.w};
+            int meta4[4] = {0, 0, 0, 0};
+            if constexpr (!DENSE) {
+              const int4 M4 = *reinterpret_cast<const int4*>(&s_meta[cc]);
+              meta4[0] = M4.x; meta4[1] = M4.y; meta4[2] = M4.z; meta4[3] = M4.w;
             }
-            pv[e] = pe; dsv[e] = de;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float sraw = __uint_as_float(sv[i + e]), dpraw = __uint_as_float(dpv[i + e]);
+              float pe, de;
+              if constexpr (!DENSE) {
+                const int kind = meta4[e] & 3, tt = meta4[e] >> 2;
+                const bool ok = key_ok && ((kind & 2) != 0 || (p.mask_mode == 1 ? tt == media_k : tt >= media_k));
+                const bool uni = kind == 2;                        // uniform row: S = 0 over all keys, no grad to q / k
+                pe = ok ? ex2_approx(fmaf(sraw, uni ? 0.f : sl2, -lse4[e])) : 0.f;
+                de = uni ? 0.f : pe * (dpraw - del4[e]) * p.scale;
+              } else {
+                const int qrow = q0 + cc + e;
+                bool masked = causal && key > qrow + off;
+                if (mask != nullptr && !masked && key_ok && lse4[e] < INFINITY)
+                  masked = mask[((long long)b * p.nq + qrow) * p.nk + key] != 0;
+                const float sc = masked ? MASKED : fmaf(sraw, sl2, slope_key);
+                pe = key_ok ? ex2_approx(sc - lse4[e]) : 0.f;
+                de = masked ? 0.f : pe * (dpraw - del4[e]) * p.scale;
+              }
+              pv[e] = pe; dsv[e] = de;
+            }
           }
-          wp[i >> 1] = pack_bf16x2(pv[0], pv[1]);
-          wd[i >> 1] = pack_bf16x2(dsv[0], dsv[1]);
+          wp[i >> 1] = pack_bf16x2(pv[0], pv[1]); wp[(i >> 1) + 1] = pack_bf16x2(pv[2], pv[3]);
+          wd[i >> 1] = pack_bf16x2(dsv[0], dsv[1]); wd[(i >> 1) + 1] = pack_bf16x2(dsv[2], dsv[3]);
         }
         // 32 query columns = four 16-byte pieces of this key row inside the 64-query atom `half`
 #pragma unroll
@@ -906,27 +1200,35 @@ static void fill_params(const Args& a, Params& p) {
   p.mask_mode = a.dense ? 0 : a.mask_mode; p.kpm = a.kpm > 0 ? a.kpm : 64; p.causal = a.causal; p.dq_direct = 0;
 }
 
+static bool fwd_v1_forced() {
+  static int mode = -1;
+  if (mode < 0) { const char* e = getenv("OFK_ATTN_FWD_V1"); mode = (e && atoi(e) != 0) ? 1 : 0; }
+  return mode == 1;
+}
+
 template <int HD, bool DENSE>
 static int launch_fwd(const Args& a) {
-  using C = FwdCfg<HD>;
+  const bool v1 = fwd_v1_forced();
+  const int bkt = v1 ? FwdCfg<HD>::BKT : Fwd2Cfg<HD>::BKT;
+  const int smem_bytes = v1 ? FwdCfg<HD>::SMEM : Fwd2Cfg<HD>::SMEM;
   CUtensorMap tq, tk, tv;
   int rc = ofk_tensor_map_bf16(a.q, a.ldq, a.batch * a.nq, a.heads * HD, 64, 128, &tq);
   if (rc) return rc;
-  rc = ofk_tensor_map_bf16(a.k, a.ldk, a.batch * a.nk, a.heads * HD, 64, C::BKT, &tk);
+  rc = ofk_tensor_map_bf16(a.k, a.ldk, a.batch * a.nk, a.heads * HD, 64, bkt, &tk);
   if (rc) return rc;
-  rc = ofk_tensor_map_bf16(a.v, a.ldv, a.batch * a.nk, a.heads * HD, 64, C::BKT, &tv);
+  rc = ofk_tensor_map_bf16(a.v, a.ldv, a.batch * a.nk, a.heads * HD, 64, bkt, &tv);
   if (rc) return rc;
-  auto kern = attn_fwd_tc_kernel<HD, DENSE>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+  auto kern = v1 ? attn_fwd_tc_kernel<HD, DENSE> : attn_fwd2_tc_kernel<HD, DENSE>;
+  static bool attr_done[2] = {false, false};
+  if (!attr_done[v1 ? 1 : 0]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return ofk_set_error(OFK_ERR_CUDA, cudaGetErrorString(e));
-    attr_done = true;
+    attr_done[v1 ? 1 : 0] = true;
   }
   Params p;
   fill_params(a, p);
   dim3 grid((a.nq + 127) / 128, a.heads, a.batch);
-  kern<<<grid, FWD_THREADS, C::SMEM, (cudaStream_t)a.stream>>>(tq, tk, tv, p);
+  kern<<<grid, FWD_THREADS, smem_bytes, (cudaStream_t)a.stream>>>(tq, tk, tv, p);
   OFK_CHECK_LAUNCH();
   ++g_tc_launches;
   return 0;

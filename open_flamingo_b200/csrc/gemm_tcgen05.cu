@@ -795,6 +795,7 @@ static int get_tensor_map(const void* ptr, long long ld, int rows, int cols, int
 }
 
 static int g_num_sms = 0;
+static int g_reserved_sms = 0;   // SMs the persistent grids leave free (ofk_gemm_reserve_sms): room for NCCL's CTAs
 
 template <int BN, int A_MN, int B_MN, int EPI>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
@@ -808,7 +809,8 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
   }
   const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
   const int work = m_tiles * n_tiles * p.splits;
-  const int grid = work < g_num_sms ? work : g_num_sms;
+  const int avail = g_num_sms - g_reserved_sms;
+  const int grid = work < avail ? work : avail;
   kern<<<grid, NUM_THREADS, L::TOTAL, stream>>>(ta, tb, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return ofk_set_error(OFK_ERR_CUDA, cudaGetErrorString(e));
@@ -827,7 +829,7 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
   }
   const int tiles2 = ((p.M + 255) / 256) * ((p.N + 255) / 256);
   const int work = p.tail_s > 0 ? p.tail_first + (tiles2 - p.tail_first) * p.tail_s : tiles2 * p.splits;
-  int clusters = g_num_sms / 2;
+  int clusters = (g_num_sms - g_reserved_sms) / 2;
   if (work < clusters) clusters = work;
   kern<<<2 * clusters, NUM_THREADS, Smem2::TOTAL, stream>>>(ta, tb, p);
   cudaError_t e = cudaGetLastError();
@@ -953,7 +955,7 @@ static int gemm_impl(int epi, int a_mn_major, int b_mn_major, const void* A, lon
     // The persistent grid walks `tiles` 256 x 256 tiles on P SM pairs; when the last round is at most half full,
     // cut its tiles into k-slices so that round costs 1/s of a tile-time (plus one fp32 partial round trip
     // through L2) instead of a whole one: e.g. the N = 2048 GEMMs of MPT-1B are 256 tiles on 74 pairs = 3.46 rounds.
-    const int P = g_num_sms / 2;
+    const int P = (g_num_sms - g_reserved_sms) / 2;
     const int tiles = ((M + 255) / 256) * ((N + 255) / 256);
     const int rem = tiles % P;
     if (rem > 0 && rem <= OFK_GEMM_WS_TILES / 2) {
@@ -1004,6 +1006,14 @@ extern "C" int ofk_gemm_bf16(int epi, int a_mn_major, int b_mn_major, const void
 }
 
 extern "C" long long ofk_gemm_workspace_bytes(void) { return OFK_GEMM_WS_BYTES; }
+
+extern "C" int ofk_gemm_reserve_sms(int n) {
+  const int prev = ofk::g_reserved_sms;
+  if (n < 0) n = 0;
+  if (n > 64) n = 64;
+  ofk::g_reserved_sms = n & ~1;   // whole SM pairs
+  return prev;
+}
 
 extern "C" int ofk_gemm_bf16_ws(int epi, int a_mn_major, int b_mn_major, const void* A, long long lda, const void* B,
                                 long long ldb, int M, int N, int K, int splits, int block_n, void* out, long long ldo,

@@ -36,14 +36,21 @@ def _gemm_workspace(device):
 
 
 _comm_in_flight = False
+# SMs every persistent GEMM grid leaves to NCCL while gradient-chunk all-reduces are in flight (0 = none); the
+# environment variable lets bench.py / a launcher pick it per run without code changes
+COMM_RESERVED_SMS = int(os.environ.get("OFK_COMM_RESERVE_SMS", "0"))
 
 
 def set_comm_in_flight(flag):
-    """train.GradBucket brackets the window in which gradient-chunk all-reduces may be running.  Inside it the GEMM
+    """train.GradBucket brackets the window in which gradient-chunk all-reduces may be running.  Inside it (a) the GEMM
     tail split is not used: its owner slice spins on flags written by OTHER clusters of the same persistent grid,
-    which assumes all clusters are co-resident -- not guaranteed while NCCL's CTAs hold SMs."""
+    which assumes all clusters are co-resident -- not guaranteed while NCCL's CTAs hold SMs; (b) the persistent GEMM
+    grids are shrunk by COMM_RESERVED_SMS so the collective's CTAs can run BESIDE the GEMMs instead of between them."""
     global _comm_in_flight
-    _comm_in_flight = bool(flag)
+    flag = bool(flag)
+    if flag != _comm_in_flight and COMM_RESERVED_SMS > 0:
+        L.lib().ofk_gemm_reserve_sms(COMM_RESERVED_SMS if flag else 0)
+    _comm_in_flight = flag
 
 
 def gemm(a, b, *, a_mn=False, b_mn=False, epi=L.EPI_STORE_BF16, out=None, out2=None, aux=None, bias=None,

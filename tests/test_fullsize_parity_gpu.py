@@ -34,7 +34,7 @@ bf16, f32 = torch.bfloat16, torch.float32
 VIT_L14 = dict(image_size=224, patch_size=14, width=1024, layers=24, heads=16, output_dim=768)
 
 
-_PREFIXES = ("vision_encoder.", "perceiver.", "lang_encoder.gated_cross_attn_layers.")
+from oracle.harness import PREFIXES as _PREFIXES  # noqa: E402
 
 
 def _rel(a, ref):
@@ -59,28 +59,9 @@ class _NoTF32:
 
 
 def _oracle_of(model, every):
-    """The oracle around a private copy of the frozen LM (plain HF model: the FlamingoLMMixin is stripped, its
-    decoder blocks restored) and a detached copy of every hot-path parameter, named as in the reference."""
-    from oracle import flamingo_oracle as O
-    lm = copy.deepcopy(model.lang_encoder)
-    blocks = [layer.decoder_layer for layer in lm._get_decoder_layers()]
-    lm._set_decoder_layers(torch.nn.ModuleList(blocks))
-    lm.__class__ = lm.__class__.__mro__[2]   # drop the mixin: plain HF LM + the oracle's pre-hooks
-    lm.gated_cross_attn_layers = None
-    lm.old_decoder_blocks = None
-    lm.__dict__.pop("loss_function", None)   # the product installs its fused loss on the instance: the oracle uses HF's
-    for p in lm.parameters():
-        p.requires_grad_(False)
-    sd = {}
-    for k, v in model.state_dict().items():
-        if k.startswith(_PREFIXES):
-            sd[k] = v.detach().clone().float()
-    # every gated block is reachable under two names (flamingo_lm.py:94-126); keep the reference's checkpoint names
-    trainable = [k for k, p in model.named_parameters(remove_duplicate=False) if p.requires_grad and k in sd]
-    for k in trainable:
-        sd[k].requires_grad_(True)
-    orc = O.OracleFlamingo(lm, blocks, sd, model.media_token_id, xattn_every=every, vit_heads=16, vit_patch=14)
-    return orc, sd, trainable
+    """The oracle around a private copy of the frozen LM and of every hot-path parameter (oracle/harness.py)."""
+    from oracle.harness import oracle_from_model
+    return oracle_from_model(model, every)
 
 
 def _hidden_grad_hooks(layers, store):
@@ -96,18 +77,12 @@ def _hidden_grad_hooks(layers, store):
 
 
 def _run_oracle(orc, sd, trainable, batch, amp):
-    for k in trainable:
-        sd[k].grad = None
     hidden = {}
     handles = _hidden_grad_hooks(orc.blocks, hidden)
+    from oracle.harness import oracle_train_step
     try:
         with _NoTF32():
-            if amp:
-                with torch.autocast("cuda", dtype=bf16):
-                    out = orc.forward(batch["vision_x"], batch["lang_x"], attention_mask=batch["attention_mask"], labels=batch["labels"])
-            else:
-                out = orc.forward(batch["vision_x"], batch["lang_x"], attention_mask=batch["attention_mask"], labels=batch["labels"])
-            out.loss.float().backward()
+            out = oracle_train_step(orc, sd, trainable, batch, amp_dtype=bf16 if amp else None)
     finally:
         for h in handles:
             h.remove()
