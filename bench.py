@@ -188,6 +188,86 @@ class GemmTimer:
         return tot_ms, tot_flop, len(self.records), by
 
 
+class GraphGemmTimer:
+    """Per-GEMM device times INSIDE a captured CUDA graph of the training step: an event-record node with the
+    cudaEventRecordExternal flag before and after every tcgen05 GEMM launch (cudart called directly on the capturing
+    stream; torch.cuda.Event cannot be recorded during capture).  Inside a graph there is no CPU between the nodes, so
+    the pairs bracket exactly the kernel (plus one node-to-node gap), unlike event pairs in an eager pass, which also
+    contain whatever time the host needs to enqueue the launch when the step is CPU-bound."""
+
+    def __init__(self):
+        import ctypes
+        self.ct = ctypes
+        self.rt = None
+        for name in ("libcudart.so.12", "libcudart.so"):
+            try:
+                self.rt = ctypes.CDLL(name)
+                break
+            except OSError:
+                continue
+        if self.rt is None:
+            raise RuntimeError("libcudart not loadable")
+        self.rt.cudaEventCreate.argtypes = [ctypes.POINTER(ctypes.c_void_p)]
+        self.rt.cudaEventRecordWithFlags.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint]
+        self.rt.cudaEventElapsedTime.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.c_void_p, ctypes.c_void_p]
+        self.rt.cudaEventDestroy.argtypes = [ctypes.c_void_p]
+        self.pairs = []      # (ev0, ev1, flop, epi, a_mn, b_mn, shape)
+        self.acc = {}        # index -> accumulated ms
+        self.replays = 0
+
+    def _event(self):
+        ev = self.ct.c_void_p()
+        if self.rt.cudaEventCreate(self.ct.byref(ev)) != 0:
+            raise RuntimeError("cudaEventCreate failed")
+        return ev
+
+    def _record(self, ev):
+        rc = self.rt.cudaEventRecordWithFlags(ev, self.ct.c_void_p(torch.cuda.current_stream().cuda_stream), 1)  # 1 = External
+        if rc != 0:
+            raise RuntimeError(f"cudaEventRecordWithFlags failed ({rc})")
+
+    def wrap(self, ops_mod):
+        timer = self
+
+        def make(orig):
+            def timed(a, b, **kw):
+                if not torch.cuda.is_current_stream_capturing():      # warm-up passes: the External flag is capture-only
+                    return orig(a, b, **kw)
+                e0, e1 = timer._event(), timer._event()
+                timer._record(e0)
+                out = orig(a, b, **kw)
+                timer._record(e1)
+                a_mn, b_mn = kw.get("a_mn", False), kw.get("b_mn", False)
+                m, k = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
+                n = b.shape[1] if b_mn else b.shape[0]
+                m, n, k = kw.get("M") or m, kw.get("N") or n, kw.get("K") or k
+                timer.pairs.append((e0, e1, 2.0 * m * n * k, kw.get("epi", 0), int(a_mn), int(b_mn), (m, n, k, kw.get("splits", 1))))
+                return out
+            return timed
+
+        self._mod = ops_mod
+        self._orig = {name: getattr(ops_mod, name) for name in ("gemm", "gemm_grouped")}
+        for name, fn in self._orig.items():
+            setattr(ops_mod, name, make(fn))
+
+    def unwrap(self):
+        for name, fn in self._orig.items():
+            setattr(self._mod, name, fn)
+
+    def collect(self):
+        """Call after each replay + synchronize: accumulate the elapsed time of every pair."""
+        ms = self.ct.c_float()
+        for i, (e0, e1, *_rest) in enumerate(self.pairs):
+            if self.rt.cudaEventElapsedTime(self.ct.byref(ms), e0, e1) != 0:
+                raise RuntimeError("cudaEventElapsedTime failed")
+            self.acc[i] = self.acc.get(i, 0.0) + ms.value
+        self.replays += 1
+
+    def records_ms(self):
+        return [(self.acc[i] / self.replays, flop, epi, a_mn, b_mn, shape)
+                for i, (_e0, _e1, flop, epi, a_mn, b_mn, shape) in enumerate(self.pairs)]
+
+
 # ----------------------------------------------------------------------------------------------- reference arm (CPU port)
 def build_cpu_oracle(model_name, seed=0):
     """Oracle (CPU fp32 port of the reference) with the bench model's architecture, random init."""
@@ -413,6 +493,7 @@ def run_ours(args):
                 graphed(resident)
     barrier()
     run_step = (lambda batch: graphed(batch)) if graphed is not None else train_step
+    graph_used = graphed is not None
 
     # ---- device-resident timing (value), clocks sampled during the timed region
     sampler = ClockSampler(local_rank)
@@ -435,9 +516,56 @@ def run_ours(args):
     ms_instr = timed(lambda: train_step(resident), args.steps)
     timer.unwrap()
     gemm_ms, gemm_flop, gemm_n, gemm_by = timer.summary()
+    gemm_steps = args.steps
+    gemm_method = "CUDA-event pair around every GEMM launch of an eager pass of the same K steps (contains host enqueue gaps when CPU-bound)"
+    shape_rows = timer.by_shape(args.steps)
+    if graphed is not None:
+        # preferred: the same pairs as external-event nodes inside a second captured graph of the step
+        try:
+            gt = GraphGemmTimer()
+            gt.wrap(ops)
+            try:
+                g2 = GraphedTrainStep(model, trainer, resident, warmup=1)
+            finally:
+                gt.unwrap()
+            if not g2.ok:
+                raise RuntimeError(g2.error)
+            for _ in range(2):
+                g2(resident)
+            torch.cuda.synchronize()
+            gt.acc, gt.replays = {}, 0
+            for _ in range(args.steps):
+                g2(resident)
+                torch.cuda.synchronize()
+                gt.collect()
+            recs = gt.records_ms()
+            gemm_ms = sum(r[0] for r in recs)
+            gemm_flop = sum(r[1] for r in recs)
+            gemm_n = len(recs)
+            gemm_steps = 1
+            gemm_by = {}
+            acc = {}
+            for ms_, flop, epi, a_mn, b_mn, shape in recs:
+                d = gemm_by.setdefault(f"epi{epi}_a{a_mn}b{b_mn}", [0.0, 0.0, 0])
+                d[0] += ms_; d[1] += flop; d[2] += 1
+                d2 = acc.setdefault((epi, a_mn, b_mn) + shape, [0.0, 0.0, 0])
+                d2[0] += ms_; d2[1] += flop; d2[2] += 1
+            shape_rows = []
+            for (epi, a_mn, b_mn, m, n, k, splits), (ms_, flop, cnt) in acc.items():
+                tiles = ((m + 255) // 256) * ((n + 255) // 256) * splits
+                shape_rows.append({"epi": epi, "a_mn": a_mn, "b_mn": b_mn, "M": m, "N": n, "K": k, "splits": splits,
+                                   "launches_per_step": cnt, "ms_per_step": ms_, "us_per_launch": 1e3 * ms_ / cnt,
+                                   "TFLOP/s": flop / (ms_ * 1e-3) / 1e12 if ms_ else 0.0, "tiles": tiles, "waves_74": tiles / 74.0})
+            shape_rows.sort(key=lambda r: -r["ms_per_step"])
+            gemm_method = ("cudaEventRecordExternal node pair around every GEMM launch INSIDE a captured CUDA graph of the step, "
+                           f"mean of {args.steps} replays")
+            del g2
+        except Exception as e:  # noqa: BLE001 - keep the eager numbers
+            if rank == 0:
+                print(f"[bench] in-graph GEMM timing unavailable ({e!r}); using the eager event pairs", file=sys.stderr)
     if args.gemm_shapes and rank == 0:
         with open(args.gemm_shapes, "w") as f:
-            json.dump(timer.by_shape(args.steps), f, indent=1)
+            json.dump(shape_rows, f, indent=1)
 
     # ---- end-to-end timing: pinned host inputs -> device every step, loss read back every step
     def e2e_step():
@@ -473,11 +601,12 @@ def run_ours(args):
                     "peak_source": peak_src, "traffic": traffic,
                     "traffic_source": "STATIC: mean dram__bytes_read+write per launch of the FFN GEMMs in the committed ncu --set full "
                                       "capture profiles/gemm_traffic.json (see its `build` field), not re-measured by this run",
-                    "launches_per_step": gemm_n / args.steps, "gemm_ms_per_step": gemm_ms / args.steps,
-                    "share_of_step": gemm_ms / ms_instr if ms_instr else None,
-                    "instrumented_ms_per_step": ms_instr / args.steps,
-                    "by_variant": {k: {"TFLOP/s": v[1] / (v[0] * 1e-3) / 1e12 if v[0] else 0.0, "ms_per_step": v[0] / args.steps,
-                                       "launches_per_step": v[2] / args.steps} for k, v in sorted(gemm_by.items())}}
+                    "launches_per_step": gemm_n / gemm_steps, "gemm_ms_per_step": gemm_ms / gemm_steps,
+                    "share_of_step": (gemm_ms / gemm_steps) / ms_step if ms_step else None,
+                    "method": gemm_method,
+                    "eager_instrumented_ms_per_step": ms_instr / args.steps,
+                    "by_variant": {k: {"TFLOP/s": v[1] / (v[0] * 1e-3) / 1e12 if v[0] else 0.0, "ms_per_step": v[0] / gemm_steps,
+                                       "launches_per_step": v[2] / gemm_steps} for k, v in sorted(gemm_by.items())}}
         gpu_eager = None
         if not args.no_gpu_eager_ref and world == 1:
             try:
@@ -501,7 +630,7 @@ def run_ours(args):
                 "config": {"workload": f"{args.model.upper()} (ViT-L/14 + {LM_NAME.get(args.model, 'tiny')}-shaped HF MptForCausalLM, xattn_every={every}) "
                                        "amp_bf16 train step: fwd+bwd+grad all-reduce+clip+AdamW",
                            "global_batch": world * B * MB, "per_gpu_batch": B, "micro_batches": MB, "t_img": T_img, "seq_len": T_txt,
-                           "parallelism": f"dp{world}", "frozen_lm_blocks": args.lm, "cuda_graph": graphed is not None, "l2": "per-step working set (>10 GB weights+activations) exceeds the 126 MB L2; no explicit flush",
+                           "parallelism": f"dp{world}", "frozen_lm_blocks": args.lm, "cuda_graph": graph_used, "l2": "per-step working set (>10 GB weights+activations) exceeds the 126 MB L2; no explicit flush",
                            "trainable_params": sum(p.numel() for p in model.parameters() if p.requires_grad)},
                 "e2e": {"value": tokens / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},

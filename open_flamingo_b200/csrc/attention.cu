@@ -618,7 +618,23 @@ extern "C" int ofk_attn_fwd(const void* q, const void* k, const void* v, void* o
     a.q_bs = q_bstride; a.ldq = ldq; a.k_bs = k_bstride; a.ldk = ldk; a.v_bs = v_bstride; a.ldv = ldv; a.o_bs = o_bstride;
     a.ldo = ldo; a.scale = scale; a.dense = 0; a.mask_mode = mask_mode; a.text_time = text_time; a.kpm = keys_per_media;
     a.stream = stream_;
-    if (tc::fwd_supported(a)) return tc::fwd(a);
+    if (tc::fwd_supported(a)) {
+      // A sequence that overhangs the last 128-query tile by a few rows (the ViT's 257 = 2 x 128 + 1 tokens) would cost
+      // a whole extra tile -- a third of the CTAs -- for those rows: the tensor-core kernel takes the full tiles and
+      // the overhanging rows go through the 64-row mma.sync kernel below (no mask, no LSE: the ViT forward).
+      const int tail = nq % 128;
+      if (nq > 128 && tail > 0 && tail <= 16 && mask_mode == 0 && lse == nullptr) {
+        a.q_tile_limit = nq / 128;
+        if (int rc = tc::fwd(a)) return rc;
+        const long long r0 = (long long)(nq - tail);
+        p.q += r0 * ldq; p.out += r0 * ldo; p.nq = tail;
+        dim3 grid_t(1, heads, batch);
+        attn_fwd_kernel<<<grid_t, ATT_THREADS, 0, (cudaStream_t)stream_>>>(p);
+        OFK_CHECK_LAUNCH();
+        return 0;
+      }
+      return tc::fwd(a);
+    }
   }
   dim3 grid((nq + BQ - 1) / BQ, heads, batch);
   attn_fwd_kernel<<<grid, ATT_THREADS, 0, (cudaStream_t)stream_>>>(p);

@@ -506,7 +506,10 @@ attn_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
   if (warp == 5 && lane == 0) {
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&k_full[i], 1); mbar_init(&s_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
-    mbar_init(p_full, 128); mbar_init(o_full, 1);
+    // softmax warps whose 32 query rows all lie outside the problem (64 Perceiver latents in a 128-row tile, the ragged
+    // last tile of a sequence) do nothing: they neither arrive on p_full nor read TMEM; their P rows stay unwritten,
+    // which only affects their own (never stored) output rows
+    mbar_init(p_full, 32 * min(4, (p.nq - q0 + 31) / 32)); mbar_init(o_full, 1);
     fence_barrier_init();
   }
   if (warp == 4) {
@@ -627,7 +630,9 @@ attn_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
     // ===================== softmax / output (thread = query row = TMEM lane) =====================
     const int row = q0 + (int)threadIdx.x;
     const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const bool warp_active = q0 + warp * 32 < p.nq;                  // warp-uniform
     float m_used = -INFINITY, l = 0.f;          // the accumulators (O in TMEM, l) are expressed relative to m_used
+    if (warp_active) {
     const uint32_t p_row = smem_u32(sP) + threadIdx.x * 128;
     const int sw = threadIdx.x & 7;
     for (int it = 0; it < nsteps; ++it) {
@@ -725,6 +730,7 @@ attn_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
       }
     }
     if (row < p.nq && p.lse != nullptr) p.lse[((long long)b * p.heads + h) * p.nq + row] = l > 0.f ? m_used + log2f(l) : 0.f;
+    }   // warp_active
   }
 
   tc_fence_before();
@@ -876,7 +882,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
       if (need) {
         if (threadIdx.x == 0 && count < C::MAXQT) s_qlist[count] = qt;
         ++count;
-      } else if (p.dq_direct && threadIdx.x < 256) {
+      } else if (p.dq_direct == 1 && threadIdx.x < 256) {
         // single-key-tile mode writes dQ straight from the accumulator, so a query tile nobody visits (e.g. 128 rows
         // before the first <image>) must get its zeros here; with the fp32 accumulator the memset provides them
         constexpr int PIECES = HD / 8;                             // 16-byte pieces per row
@@ -1088,7 +1094,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
                 v.y = pack_bf16x2(__uint_as_float(acc[8 * j + 2]), __uint_as_float(acc[8 * j + 3]));
                 v.z = pack_bf16x2(__uint_as_float(acc[8 * j + 4]), __uint_as_float(acc[8 * j + 5]));
                 v.w = pack_bf16x2(__uint_as_float(acc[8 * j + 6]), __uint_as_float(acc[8 * j + 7]));
-                *reinterpret_cast<uint4*>(g + 8 * j) = v;
+                if (p.dq_direct == 1) {
+                  *reinterpret_cast<uint4*>(g + 8 * j) = v;
+                } else {   // 2..4 key tiles: accumulate straight into the (pre-zeroed) bf16 dQ, 8 elements per red
+                  asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(g + 8 * j), "r"(v.x), "r"(v.y),
+                               "r"(v.z), "r"(v.w)
+                               : "memory");
+                }
               }
             } else {
               float* g = p.dq32 + ((long long)b * p.nq + qrow) * ((long long)p.heads * HD) + h * HD + col;
@@ -1175,16 +1187,26 @@ bool fwd_supported(const Args& a) {
   if (!common_supported(a)) return false;
   return aligned16(a.out) && a.ldo % 8 == 0 && a.o_bs % 8 == 0;
 }
+// dQ gets one partial per 128-key tile.  One tile: stored directly.  2..4 tiles (the LM at T_txt <= 512, 2..5 images of
+// 64 latents): bf16 reductions (red.global.add.noftz.bf16x2) into the zero-filled dQ itself -- at most three extra bf16
+// roundings, no scratch, no conversion pass.  More tiles (the 4160-key Perceiver isolation shape): fp32 accumulator.
+constexpr int BF16_ATOMIC_MAX_KEYS = 512;
 long long bwd_workspace_bytes(int batch, int heads, int hd, int nq, int nk) {
-  if (nk <= 128) return 0;   // a single key tile: dQ is written directly
+  if (nk <= BF16_ATOMIC_MAX_KEYS) return 0;
   return (long long)batch * nq * heads * hd * 4;
 }
 bool bwd_supported(const Args& a) {
   if (!common_supported(a)) return false;
+  // The backward CTA owns 128 KEYS and visits the query tiles that see them.  With at most 64 query rows per (batch,
+  // head) -- the 64 Perceiver latents, a decode step -- there is a single, half-empty query tile: every CTA runs one
+  // iteration and is all prologue / epilogue (measured on the 4160-key isolation shape: 1164 us against 778 us for the
+  // 64-row mma.sync kernels, profiles/r02_attention_by_shape.md).  Those problems keep the mma.sync backward.
+  if (a.nq <= 64) return false;
   if (a.o_bs != (long long)a.nq * a.ldo || !aligned16(a.d_o) || a.ldo % 8 != 0) return false;
   if (!aligned16(a.dq) || !aligned16(a.dk) || !aligned16(a.dv)) return false;
   if ((a.lddq | a.lddk | a.lddv | a.dq_bs | a.dk_bs | a.dv_bs) % 8 != 0) return false;
   if ((a.nq + 127) / 128 > BwdCfg<64>::MAXQT) return false;
+  if (a.nk > 128 && a.nk <= BF16_ATOMIC_MAX_KEYS && a.dq_bs != (long long)a.nq * a.lddq) return false;   // 2-D memset of dQ
   const long long need = bwd_workspace_bytes(a.batch, a.heads, a.hd, a.nq, a.nk);
   if (need > 0 && (a.workspace == nullptr || a.workspace_bytes < need || !aligned16(a.workspace))) return false;
   return true;
@@ -1227,7 +1249,9 @@ static int launch_fwd(const Args& a) {
   }
   Params p;
   fill_params(a, p);
-  dim3 grid((a.nq + 127) / 128, a.heads, a.batch);
+  int q_tiles = (a.nq + 127) / 128;
+  if (a.q_tile_limit > 0 && a.q_tile_limit < q_tiles) q_tiles = a.q_tile_limit;
+  dim3 grid(q_tiles, a.heads, a.batch);
   kern<<<grid, FWD_THREADS, smem_bytes, (cudaStream_t)a.stream>>>(tq, tk, tv, p);
   OFK_CHECK_LAUNCH();
   ++g_tc_launches;
@@ -1266,8 +1290,11 @@ static int launch_bwd(const Args& a) {
                                                                    a.delta, a.batch, a.heads, a.nq, a.o_bs, a.ldo);
   OFK_CHECK_LAUNCH();
   const long long ws = bwd_workspace_bytes(a.batch, a.heads, HD, a.nq, a.nk);
-  p.dq_direct = ws == 0 ? 1 : 0;
-  if (ws > 0) {
+  p.dq_direct = a.nk <= 128 ? 1 : (ws == 0 ? 2 : 0);
+  if (p.dq_direct == 2) {
+    cudaError_t e = cudaMemset2DAsync(a.dq, (size_t)a.lddq * 2, 0, (size_t)a.heads * HD * 2, (size_t)a.batch * a.nq, stream);
+    if (e != cudaSuccess) return ofk_set_error(OFK_ERR_CUDA, cudaGetErrorString(e));
+  } else if (ws > 0) {
     cudaError_t e = cudaMemsetAsync(a.workspace, 0, (size_t)ws, stream);
     if (e != cudaSuccess) return ofk_set_error(OFK_ERR_CUDA, cudaGetErrorString(e));
   }

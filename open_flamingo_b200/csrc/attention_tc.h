@@ -20,6 +20,7 @@ struct Args {
   int causal; const unsigned char* mask; const float* slopes; const int* pure_causal;
   void* workspace; long long workspace_bytes;   // backward: fp32 dQ accumulator (see bwd_workspace_bytes)
   void* stream;
+  int q_tile_limit;                // forward: > 0 = only the first q_tile_limit 128-query tiles (the caller covers the tail rows)
 };
 
 // true when the tensor-core kernels can run this problem (TMA-describable layout, supported head_dim); depends only
