@@ -73,7 +73,7 @@ int ofk_gemm_bf16(int epi, int a_mn_major, int b_mn_major, const void* A, long l
  * 3.46 rounds), its tiles are cut into 2-4 k-slices that run on the otherwise idle SM pairs; the slices exchange fp32
  * partial accumulators through `workspace` (L2-resident) and the last slice applies the fused epilogue, so results
  * do not depend on whether the split is taken beyond fp32 summation order.  `workspace` must hold at least
- * ofk_gemm_workspace_bytes() bytes, be 16-byte aligned, have its first 4096 bytes zeroed once before first use, and
+ * ofk_gemm_workspace_bytes() bytes, be 16-byte aligned, have its first 16384 bytes zeroed once before first use, and
  * must not be shared by GEMMs that may run concurrently (one buffer per stream).  NULL = plain ofk_gemm_bf16.
  * Replaces the same reference lines as ofk_gemm_bf16. */
 long long ofk_gemm_workspace_bytes(void);

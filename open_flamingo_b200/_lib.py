@@ -9,7 +9,10 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libofk.so")
+# OFK_LIB_VARIANT=<name> loads open_flamingo_b200/libofk_<name>.so instead (A/B builds of a kernel made with
+# tools/build_variant.sh; measurement tooling only -- the default and every test use libofk.so)
+_VARIANT = os.environ.get("OFK_LIB_VARIANT", "")
+LIB_PATH = os.path.join(_HERE, f"libofk_{_VARIANT}.so" if _VARIANT else "libofk.so")
 
 c_void_p = ctypes.c_void_p
 c_int = ctypes.c_int

@@ -491,20 +491,41 @@ struct Smem2 {
   static constexpr int A_BYTES = BM * BK * 2;        // 16 KiB : this CTA's 128 rows of A
   static constexpr int B_BYTES = 128 * BK * 2;       // 16 KiB : this CTA's 128 rows of B
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-#ifndef OFK_STAGES2
-#define OFK_STAGES2 6
+#ifndef OFK_EPI_WARPS2
+#define OFK_EPI_WARPS2 12
 #endif
-  static constexpr int STAGES = OFK_STAGES2;
+#ifndef OFK_EPI_WARPS2_RESID
+#define OFK_EPI_WARPS2_RESID 8
+#endif
   static constexpr int BAR_BYTES = 256;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + NUM_EPI_WARPS * 32 * 128 + 1024;
+};
+// Epilogue warps of the 2-CTA kernel.  A lane quarter's 256 accumulator columns are 8 rounds of 32; with EW warps the
+// EW / 4 warps of a quarter take the rounds round-robin (8 warps: 4 rounds each; 12: 3 / 3 / 2; 16: 2 each).  More warps
+// per scheduler hide the tcgen05.ld -> staging -> math -> staging -> global chain of a round behind each other; the
+// register budget per thread shrinks accordingly (8 warps: 168, 12: 128), which the fp32-residual epilogues feel first
+// (OFK_EPI_WARPS2_RESID picks their count separately).  Same-box A/B over the 751 GEMM launches of an OF-3B step
+// (tools/bench_gemm_step.py, profiles/r02_gemm_epilogue_warps.md): 8 warps everywhere 83.7 ms; 12 everywhere 83.9-85.6 ms
+// (GELU / dGELU / QuickGELU epilogues 3-8 % faster, fp32-residual ones 6-17 % slower); 16 everywhere 86.3 ms; 12 for the
+// math epilogues + 8 for the residual ones 83.3 ms -- the default.  The TMA ring is 6 stages with 8 epilogue warps and 5 with more
+// (the per-warp staging tiles take the 32 KiB; round 1 measured 5 and 6 stages equal at K = 8192: 1621 vs ~1620 TF/s).
+template <int EPI>
+struct Epi2Cfg {
+  static constexpr bool RESID = EPI == OFK_EPI_GATE_RESID_F32 || EPI == OFK_EPI_BIAS_RESID_F32;
+  static constexpr int EW = RESID ? OFK_EPI_WARPS2_RESID : OFK_EPI_WARPS2;
+  static constexpr int THREADS = (EW + 4) * 32;
+  static constexpr int WARP_TMA = EW, WARP_MMA = EW + 1, WARP_TMEM = EW + 2;
+  static constexpr int STAGES = EW <= 8 ? 6 : 5;
+  static constexpr int TOTAL = STAGES * Smem2::STAGE_BYTES + Smem2::BAR_BYTES + EW * 32 * 128 + 1024;
 };
 
 template <int A_MN, int B_MN, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Epi2Cfg<EPI>::THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
              const GemmParams p) {
   using L = Smem2;
-  constexpr int STAGES = L::STAGES;
+  using E = Epi2Cfg<EPI>;
+  constexpr int STAGES = E::STAGES;
+  constexpr int EPI_WARPS2 = E::EW;
   constexpr int BN2 = 256;
   constexpr uint32_t TMEM_COLS = 2 * BN2;
 
@@ -529,16 +550,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
   const int first_work = (int)cluster_id_x();
   const int work_stride = (int)num_clusters_x();
 
-  if (warp == WARP_TMA && lane == 0) {
+  if (warp == E::WARP_TMA && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
   }
-  if (warp == WARP_MMA && lane == 0) {
+  if (warp == E::WARP_MMA && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 2 * NUM_EPI_WARPS); }  // both CTAs' warps
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 2 * EPI_WARPS2); }  // both CTAs' warps
     fence_barrier_init();
   }
-  if (warp == WARP_TMEM) {
+  if (warp == E::WARP_TMEM) {
     tmem_alloc_2cta(tmem_ptr, TMEM_COLS);
     tmem_relinquish_2cta();
   }
@@ -548,7 +569,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == WARP_TMA) {
+  if (warp == E::WARP_TMA) {
     // ===================== TMA producer (one thread per CTA) =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
@@ -581,7 +602,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
       }
     }
     __syncwarp();
-  } else if (warp == WARP_MMA) {
+  } else if (warp == E::WARP_MMA) {
     // ===================== MMA issuer (one thread of the leader CTA) =====================
     if (leader && lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(256, BN2, A_MN, B_MN);
@@ -614,10 +635,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
       }
     }
     __syncwarp();
-  } else if (warp < NUM_EPI_WARPS) {
-    // ===================== epilogue (8 warps per CTA; this CTA's 128 rows) =====================
-    const int q = warp & 3;
-    const int half = warp >> 2;
+  } else if (warp < EPI_WARPS2) {
+    // ===================== epilogue (EPI_WARPS2 warps per CTA; this CTA's 128 rows) =====================
+    const int q = warp & 3;                    // TMEM lane quarter == warp % 4
+    const int t3 = warp >> 2;                  // which of the quarter's warps: takes rounds t3, t3 + W, t3 + 2W, ...
+    constexpr int WPQ = EPI_WARPS2 / 4;        // warps per quarter
     float gate_t = 1.0f;
     if constexpr (EPI == OFK_EPI_GATE_RESID_F32) {
       if (p.gate != nullptr) gate_t = tanhf(__ldg(p.gate));
@@ -627,28 +649,29 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
       const Work2 wk = decode_work2(p, w, m_tiles, n_tiles, total_kb);
       const int mt = wk.mt, nt = wk.nt;
       const int n0 = nt * BN2;
-      const int wslot = (int)cta_rank * NUM_EPI_WARPS + warp;   // this warp's slot inside a tile's partials / flags
+      // tail-split partials / flags are indexed per (CTA, lane quarter, round): one producer and one consumer warp each
+      const int fslot = (int)cta_rank * 32 + q * 8;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN2 + half * (BN2 / 2);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN2;
       if (wk.role == 1) {
-        // ---- tail-split producer: dump this warp's 32 x 128 fp32 accumulators in register order, then signal
-        float* wsp = p.tail_ws + ((size_t)(wk.t * (p.tail_s - 1) + wk.j) * (2 * NUM_EPI_WARPS) + wslot) * 4096 + lane * 4;
+        // ---- tail-split producer: dump this warp's rounds (32 x 32 fp32 each) in register order, then signal per round
 #pragma unroll 1
-        for (int c = 0; c < BN2 / 64; ++c) {
+        for (int r = t3; r < BN2 / 32; r += WPQ) {
+          float* wsp = p.tail_ws + ((size_t)(wk.t * (p.tail_s - 1) + wk.j) * 64 + fslot + r) * 1024 + lane * 4;
           uint32_t acc[32];
-          tmem_ld16(taddr + c * 32, *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));
-          tmem_ld16(taddr + c * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&acc[16]));
+          tmem_ld16(taddr + r * 32, *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));
+          tmem_ld16(taddr + r * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&acc[16]));
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            st_global_cg_v4(wsp + c * 1024 + i * 128, make_uint4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]));
-        }
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) {
+            st_global_cg_v4(wsp + i * 128, make_uint4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]));
           __threadfence();
-          atomicAdd(p.tail_flags + wk.t * (2 * NUM_EPI_WARPS) + wslot, 1);
+          __syncwarp();
+          if (lane == 0) {
+            __threadfence();
+            atomicAdd(p.tail_flags + wk.t * 64 + fslot + r, 1);
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -660,39 +683,35 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
       const int row0 = mt * 256 + (int)cta_rank * 128 + q * 32;
       constexpr int AUXB = AuxBytes<EPI>::value;
       uint4 pre[AUXB ? AUXB * 2 : 1];
-      const int colbase = n0 + half * (BN2 / 2);
       if constexpr (AUXB != 0) {
-        if (row0 < p.M && colbase < p.N) aux_prefetch<AUXB>(pre, p.aux, p.ldaux, row0, colbase, p.M, p.N);
-      }
-      const float* wsp = nullptr;
-      if (wk.role == 2) {
-        // ---- tail-split owner: wait until the other slices' partials for this warp slot have landed
-        int* flag = p.tail_flags + wk.t * (2 * NUM_EPI_WARPS) + wslot;
-        if (lane == 0) {
-          while (ld_acquire_gpu(flag) < p.tail_s - 1) __nanosleep(64);
-          *flag = 0;                                   // single consumer: ready for the next launch
-        }
-        __syncwarp();
-        __threadfence();
-        wsp = p.tail_ws + ((size_t)(wk.t * (p.tail_s - 1)) * (2 * NUM_EPI_WARPS) + wslot) * 4096 + lane * 4;
+        if (row0 < p.M && n0 + t3 * 32 < p.N) aux_prefetch<AUXB>(pre, p.aux, p.ldaux, row0, n0 + t3 * 32, p.M, p.N);
       }
 #pragma unroll 1
-      for (int c = 0; c < BN2 / 64; ++c) {      // 32 columns per round: two TMEM loads in flight per wait
+      for (int r = t3; r < BN2 / 32; r += WPQ) {      // 32 columns per round: two TMEM loads in flight per wait
         uint32_t acc[32];
-        tmem_ld16(taddr + c * 32, *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));
-        tmem_ld16(taddr + c * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&acc[16]));
-        const int col = colbase + c * 32;
+        tmem_ld16(taddr + r * 32, *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));
+        tmem_ld16(taddr + r * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&acc[16]));
+        const int col = n0 + r * 32;
         const bool live = row0 < p.M && col < p.N;                                   // warp-uniform
         uint32_t aux_row[AUXB ? AUXB * 8 : 1];
         if constexpr (AUXB != 0) {
           if (live) aux_commit<AUXB>(stage_addr, pre, aux_row);
-          if (c + 1 < BN2 / 64 && row0 < p.M && col + 32 < p.N)                  // next round's operand: in flight
-            aux_prefetch<AUXB>(pre, p.aux, p.ldaux, row0, col + 32, p.M, p.N);       // during this round's math+stores
+          if (r + WPQ < BN2 / 32 && row0 < p.M && col + WPQ * 32 < p.N)              // next round's operand: in flight
+            aux_prefetch<AUXB>(pre, p.aux, p.ldaux, row0, col + WPQ * 32, p.M, p.N); // during this round's math+stores
         }
         tmem_ld_wait();
-        if (wsp != nullptr) {
+        if (wk.role == 2) {
+          // ---- tail-split owner: wait until the other slices' partials for this (quarter, round) have landed
+          int* flag = p.tail_flags + wk.t * 64 + fslot + r;
+          if (lane == 0) {
+            while (ld_acquire_gpu(flag) < p.tail_s - 1) __nanosleep(64);
+            *flag = 0;                                   // single consumer: ready for the next launch
+          }
+          __syncwarp();
+          __threadfence();
+          const float* wsp = p.tail_ws + ((size_t)(wk.t * (p.tail_s - 1)) * 64 + fslot + r) * 1024 + lane * 4;
           for (int j = 0; j < p.tail_s - 1; ++j) {
-            const float* pj = wsp + (size_t)j * (2 * NUM_EPI_WARPS) * 4096 + c * 1024;
+            const float* pj = wsp + (size_t)j * 64 * 1024;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const uint4 u = ld_global_cg_v4(pj + i * 128);
@@ -707,7 +726,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(&tmem_empty[as], 0);   // the leader's MMA thread waits for all 16 warps
+      if (lane == 0) mbar_arrive_cluster(&tmem_empty[as], 0);   // the leader's MMA thread waits for all 2 x EPI_WARPS2 warps
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   }
@@ -715,7 +734,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();   // neither CTA may free TMEM / exit while its peer can still touch it
-  if (warp == WARP_TMEM) {
+  if (warp == E::WARP_TMEM) {
     tc_fence_after();
     tmem_dealloc_2cta(tmem_base, TMEM_COLS);
   }
@@ -823,7 +842,7 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
   auto kern = gemm2_kernel<A_MN, B_MN, EPI>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Epi2Cfg<EPI>::TOTAL);
     if (e != cudaSuccess) return ofk_set_error(OFK_ERR_CUDA, cudaGetErrorString(e));
     attr_done = true;
   }
@@ -831,7 +850,7 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
   const int work = p.tail_s > 0 ? p.tail_first + (tiles2 - p.tail_first) * p.tail_s : tiles2 * p.splits;
   int clusters = (g_num_sms - g_reserved_sms) / 2;
   if (work < clusters) clusters = work;
-  kern<<<2 * clusters, NUM_THREADS, Smem2::TOTAL, stream>>>(ta, tb, p);
+  kern<<<2 * clusters, Epi2Cfg<EPI>::THREADS, Epi2Cfg<EPI>::TOTAL, stream>>>(ta, tb, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return ofk_set_error(OFK_ERR_CUDA, cudaGetErrorString(e));
   ofk_count_launch();
@@ -901,7 +920,7 @@ int ofk_tensor_map_bf16(const void* ptr, long long ld, int rows, int cols, int b
 // Tail-split workspace: 4 KiB of per-warp flags (zero before first use; self-resetting) + one 256 x 256 fp32
 // partial per producer slice.  rem <= P / 2 = 37 tiles and rem * (s - 1) < P = 74 partials on a 148-SM part.
 constexpr int OFK_GEMM_WS_TILES = 74;
-constexpr long long OFK_GEMM_WS_FLAG_BYTES = 4096;
+constexpr long long OFK_GEMM_WS_FLAG_BYTES = 16384;   // 64 flags (2 CTAs x 4 lane quarters x 8 rounds) per tail tile, <= 37 tiles
 constexpr long long OFK_GEMM_WS_BYTES = OFK_GEMM_WS_FLAG_BYTES + (long long)OFK_GEMM_WS_TILES * 256 * 256 * 4;
 constexpr int TAIL_MIN_KB = 48;   // below ~3k of K half a tile-time is not worth the partial round trip
 static bool tail_split_enabled() {

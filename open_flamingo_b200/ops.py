@@ -30,7 +30,7 @@ def _gemm_workspace(device):
     ws = _gemm_ws.get(key)
     if ws is None:
         ws = torch.empty(int(L.lib().ofk_gemm_workspace_bytes()), device=device, dtype=torch.uint8)
-        ws[:4096].zero_()   # the flag words; they reset themselves after every use
+        ws[:16384].zero_()   # the flag words (first 16 KiB); they reset themselves after every use
         _gemm_ws[key] = ws
     return ws
 

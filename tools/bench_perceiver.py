@@ -30,11 +30,35 @@ for _ in range(int(os.environ.get("WARM", 3))):
     step()
 torch.cuda.synchronize()
 l0 = _lib.launch_count()
+step()
+launches = _lib.launch_count() - l0
+# the 190 launches of a forward + backward are captured once and replayed (as bench.py does for the training step): an
+# eager pass on a busy host is bound by the Python / ctypes time per launch, not by the kernels
+graph = None
+if os.environ.get("GRAPH", "1") == "1":
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step()
+        graph.replay()
+        torch.cuda.synchronize()
+    except Exception as e:  # noqa: BLE001
+        print(f"[bench_perceiver] CUDA-graph capture unavailable ({e!r}); timing eagerly", file=sys.stderr)
+        graph = None
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 iters = int(os.environ.get("ITERS", 5))
 e0.record()
 for _ in range(iters):
-    step()
+    if graph is not None:
+        graph.replay()
+    else:
+        step()
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / iters
@@ -49,4 +73,4 @@ except Exception:
 peak = peaks.get("bf16_tflops", 1590.0)
 print(json.dumps({"workload": "PerceiverResampler isolation C5", "images": U, "visual_tokens": v, "dim": D, "latents": n,
                   "depth": depth, "ms_fwd_bwd": ms, "algorithmic_TFLOP": flops / 1e12, "achieved_TFLOPs": flops / ms / 1e9,
-                  "peak_TFLOPs": peak, "frac": flops / ms / 1e9 / peak, "launches_per_step": (_lib.launch_count() - l0) / iters}))
+                  "peak_TFLOPs": peak, "frac": flops / ms / 1e9 / peak, "launches_per_step": launches, "cuda_graph": graph is not None}))
