@@ -407,6 +407,8 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        from open_flamingo_b200.train import configure_nccl_for_overlap
+        configure_nccl_for_overlap()
         dist.init_process_group("nccl", device_id=dev)
 
     from open_flamingo_b200 import lm_blocks

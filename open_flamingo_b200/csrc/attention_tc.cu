@@ -11,12 +11,13 @@
 // Semantics, arguments and outputs are those of the mma.sync kernels in attention.cu / attention_dense.cu, which
 // stay as the path for layouts TMA cannot describe; LSE is log2-domain (m + log2 l) in both families.
 //
-// Forward  (CTA = 128 queries of one (batch, head); 192 threads; 2 CTAs / SM)
-//   warp 4 lane 0 : TMA producer (Q once; K_j, V_j per key tile of BKT = 8192 / head_dim keys) + TMEM alloc (256 cols)
-//   warp 5 lane 0 : MMA issuer   S_j = Q K_j^T (K-major A and B) ; O += P_j V_j (A = P from smem, B = V MN-major)
-//   warps 0-3     : thread = query row = TMEM lane.  pass 1: row max of the masked, scaled S_j; rescale the O
-//                   accumulator in TMEM (tcgen05.ld / st) when the running max moved; pass 2: p = exp2(s - m) as
-//                   bf16 into the K-major SW128 layout; finally O / l -> global, LSE.
+// Forward  (CTA = 128 queries of one (batch, head); 192 threads; 2 CTAs / SM; 64-key tiles)
+//   warp 4 lane 0 : TMA producer (Q once; a 2-stage ring of K tiles, V tiles) + TMEM alloc (256 cols)
+//   warp 5 lane 0 : MMA issuer   S_j = Q K_j^T into a DOUBLE-BUFFERED S (S_{j+1} is issued while the softmax warps work on
+//                   S_j) ; O += P_j V_j (A = P from smem, B = V through the MN-major descriptor)
+//   warps 0-3     : thread = query row = TMEM lane.  One TMEM read of the tile's 64 scores into registers, mask / scale,
+//                   p = exp2(s - m) as bf16 into the K-major SW128 layout; the running output in TMEM is rescaled lazily
+//                   (only when a row maximum grew by more than 2^8); finally O / l -> global, LSE.
 // Backward (CTA = 128 keys of one (batch, head), loop over the query tiles that can see them; 320 threads; 1 CTA / SM)
 //   warp 8 lane 0 : TMA (K, V once; Q_i, dO_i per query tile) + TMEM alloc (512 cols)
 //   warp 9 lane 0 : MMA  S^T = K Q_i^T, dP^T = V dO_i^T  ->  [threads]  ->  dV += P^T dO_i, dK += dS^T Q_i,
@@ -95,25 +96,6 @@ __device__ __forceinline__ bool media_allowed(int mask_mode, int kind, int tt, i
 }
 
 // ================================================================================================ forward
-template <int HD>
-struct FwdCfg {
-  static constexpr int BKT = HD == 64 ? 128 : 64;     // keys per tile
-  static constexpr int ATOMS = HD / 64;               // 64-wide (128-byte) head-dim atoms
-  static constexpr int Q_ATOM = 128 * 128;            // bytes of a [128 rows x 64 bf16] swizzled block
-  static constexpr int KV_ATOM = BKT * 128;
-  static constexpr int Q_BYTES = ATOMS * Q_ATOM;
-  static constexpr int KV_BYTES = ATOMS * KV_ATOM;
-  static constexpr int P_ATOMS = BKT / 64;
-  static constexpr int P_BYTES = P_ATOMS * Q_ATOM;
-  static constexpr int OFF_Q = 0;
-  static constexpr int OFF_K = OFF_Q + Q_BYTES;
-  static constexpr int OFF_V = OFF_K + KV_BYTES;
-  static constexpr int OFF_P = OFF_V + KV_BYTES;
-  static constexpr int OFF_BAR = OFF_P + P_BYTES;
-  static constexpr int SMEM = OFF_BAR + 256 + 1024;
-  static constexpr uint32_t TMEM_COLS = 256;          // S: columns [0, BKT); O: columns [128, 128 + HD)
-  static constexpr uint32_t O_COL = 128;
-};
 constexpr int FWD_THREADS = 192;
 
 template <bool DENSE>
@@ -168,288 +150,9 @@ __device__ __forceinline__ void scores16(const Params& p, const RowCtx<DENSE>& r
   }
 }
 
-template <int HD, bool DENSE>
-__global__ void __launch_bounds__(FWD_THREADS, 2)
-attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
-                   const __grid_constant__ CUtensorMap tma_v, const Params p) {
-  using C = FwdCfg<HD>;
-  constexpr int BKT = C::BKT;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem + C::OFF_Q;
-  uint8_t* sK = smem + C::OFF_K;
-  uint8_t* sV = smem + C::OFF_V;
-  uint8_t* sP = smem + C::OFF_P;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
-  uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;
-  uint64_t* v_full = bars + 2;
-  uint64_t* s_full = bars + 3;
-  uint64_t* p_full = bars + 4;
-  uint64_t* o_full = bars + 5;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
-  int* s_range = reinterpret_cast<int*>(bars + 10);   // [0] min tt, [1] max tt, [2] any uniform row
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-
-  if (threadIdx.x == 0) { s_range[0] = 1 << 30; s_range[1] = -1; s_range[2] = 0; }
-  if (warp == 5 && lane == 0) {
-    mbar_init(q_full, 1); mbar_init(k_full, 1); mbar_init(v_full, 1);
-    mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_full, 1);
-    fence_barrier_init();
-  }
-  if (warp == 4) {
-    if (lane == 0) { tma_prefetch_desc(&tma_q); tma_prefetch_desc(&tma_k); tma_prefetch_desc(&tma_v); }
-    __syncwarp();
-    tmem_alloc(tmem_ptr, C::TMEM_COLS);
-    tmem_relinquish();
-  }
-  __syncthreads();
-
-  // ---- per-row context + the key range this query tile needs (block-uniform)
-  bool causal = false;
-  const unsigned char* mask = nullptr;
-  if constexpr (DENSE) {
-    causal = p.causal != 0; mask = p.mask;
-    if (p.pure_causal != nullptr && *p.pure_causal != 0) { mask = nullptr; causal = true; }
-  }
-  RowCtx<DENSE> rc;
-  if constexpr (!DENSE) {
-    rc.kind = 1; rc.tt = 0; rc.z = 0.f;
-    if (warp < 4) {
-      const MediaRow r = classify(p, b, q0 + threadIdx.x);
-      rc.kind = r.kind; rc.tt = r.tt;
-      rc.z = r.kind == 2 ? 0.f : p.scale * LOG2E;                // uniform rows: S = 0 over every key
-      if (p.mask_mode != 0) {
-        if (r.kind == 0) { atomicMin(&s_range[0], r.tt); atomicMax(&s_range[1], r.tt); }
-        if (r.kind == 2) s_range[2] = 1;
-      }
-    }
-  } else {
-    const int row = q0 + (int)threadIdx.x;
-    rc.valid = warp < 4 && row < p.nq;
-    rc.causal_last = causal ? row + (p.nk - p.nq) : 0x7fffffff;
-    rc.mrow = (mask != nullptr && rc.valid) ? mask + ((long long)b * p.nq + row) * p.nk : nullptr;
-    rc.sl2 = p.scale * LOG2E;
-    rc.slope2 = p.slopes != nullptr ? p.slopes[h] * LOG2E : 0.f;
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-  int lo = 0, hi = p.nk;
-  if constexpr (!DENSE) {
-    if (p.mask_mode != 0 && s_range[2] == 0) {
-      if (s_range[1] < 0) { lo = 0; hi = 0; }                     // only zero rows
-      else {
-        hi = min(p.nk, s_range[1] * p.kpm);
-        lo = p.mask_mode == 1 ? max(0, (s_range[0] - 1) * p.kpm) : 0;
-      }
-    }
-  } else {
-    if (causal && mask == nullptr) hi = max(0, min(p.nk, min(q0 + 127, p.nq - 1) + (p.nk - p.nq) + 1));
-  }
-  const int t_lo = lo / BKT, t_hi = (hi + BKT - 1) / BKT;
-  const int nsteps = max(0, t_hi - t_lo);
-
-  if (warp == 4) {
-    // ===================== TMA producer =====================
-    if (lane == 0 && nsteps > 0) {
-      mbar_arrive_expect_tx(q_full, C::Q_BYTES);
-#pragma unroll
-      for (int a = 0; a < C::ATOMS; ++a) tma_load_2d(sQ + a * C::Q_ATOM, &tma_q, q_full, h * HD + 64 * a, b * p.nq + q0);
-      for (int it = 0; it < nsteps; ++it) {
-        const int key0 = (t_lo + it) * BKT;
-        if (it > 0) mbar_wait(s_full, (it - 1) & 1);              // S_{it-1} retired: K buffer is free
-        mbar_arrive_expect_tx(k_full, C::KV_BYTES);
-#pragma unroll
-        for (int a = 0; a < C::ATOMS; ++a) tma_load_2d(sK + a * C::KV_ATOM, &tma_k, k_full, h * HD + 64 * a, b * p.nk + key0);
-        if (it > 0) mbar_wait(o_full, (it - 1) & 1);              // P V_{it-1} retired: V buffer is free
-        mbar_arrive_expect_tx(v_full, C::KV_BYTES);
-#pragma unroll
-        for (int a = 0; a < C::ATOMS; ++a) tma_load_2d(sV + a * C::KV_ATOM, &tma_v, v_full, h * HD + 64 * a, b * p.nk + key0);
-      }
-    }
-    __syncwarp();
-  } else if (warp == 5) {
-    // ===================== MMA issuer =====================
-    if (lane == 0 && nsteps > 0) {
-      const uint32_t aq = smem_u32(sQ), ak = smem_u32(sK), av = smem_u32(sV), ap = smem_u32(sP);
-      auto issue_s = [&](int it) {
-        const int key0 = (t_lo + it) * BKT;
-        const int n_eff = min(BKT, ((p.nk - key0) + 15) & ~15);
-        const uint32_t idesc = make_idesc_bf16(128, n_eff, 0, 0);
-#pragma unroll
-        for (int kk = 0; kk < HD / 16; ++kk)
-          umma_bf16(tmem_base, make_smem_desc_sw128(aq + (kk >> 2) * C::Q_ATOM + (kk & 3) * 32, 0, 1024),
-                    make_smem_desc_sw128(ak + (kk >> 2) * C::KV_ATOM + (kk & 3) * 32, 0, 1024), idesc, kk > 0 ? 1u : 0u);
-        umma_commit(s_full);
-      };
-      mbar_wait(q_full, 0);
-      mbar_wait(k_full, 0);
-      tc_fence_after();
-      issue_s(0);
-      for (int it = 0; it < nsteps; ++it) {
-        const int key0 = (t_lo + it) * BKT;
-        const int n_eff = min(BKT, ((p.nk - key0) + 15) & ~15);
-        mbar_wait(p_full, it & 1);                                // P_it in smem, S_it consumed, O rescaled
-        mbar_wait(v_full, it & 1);
-        tc_fence_after();
-        constexpr uint32_t idesc_o = make_idesc_bf16(128, HD, 0, 1);
-        for (int ks = 0; ks < n_eff / 16; ++ks)                   // A = P (K-major), B = V (MN-major: 16 key rows / step)
-          umma_bf16(tmem_base + C::O_COL, make_smem_desc_sw128(ap + (ks >> 2) * C::Q_ATOM + (ks & 3) * 32, 0, 1024),
-                    make_smem_desc_sw128(av + ks * 2048, C::KV_ATOM, 1024), idesc_o, (it > 0 || ks > 0) ? 1u : 0u);
-        umma_commit(o_full);
-        if (it + 1 < nsteps) {
-          mbar_wait(k_full, (it + 1) & 1);
-          tc_fence_after();
-          issue_s(it + 1);
-        }
-      }
-    }
-    __syncwarp();
-  } else {
-    // ===================== softmax / output (thread = query row = TMEM lane) =====================
-    const int row = q0 + (int)threadIdx.x;
-    const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
-    float m = -INFINITY, l = 0.f;
-    const uint32_t p_row = smem_u32(sP) + threadIdx.x * 128;
-    const int sw = threadIdx.x & 7;
-    for (int it = 0; it < nsteps; ++it) {
-      const int key0 = (t_lo + it) * BKT;
-      const int n_eff = min(BKT, ((p.nk - key0) + 15) & ~15);
-      const int nchunks = (n_eff + 31) >> 5;
-      mbar_wait(s_full, it & 1);
-      tc_fence_after();
-      // ---- pass 1: masked / scaled row maximum
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < nchunks; ++c) {
-        uint32_t acc[32];
-        const bool two = (c * 32 + 16) < n_eff;                   // warp-uniform
-        tmem_ld16(t_row + c * 32, *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));
-        if (two) tmem_ld16(t_row + c * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&acc[16]));
-        tmem_ld_wait();
-        float s[16];
-        scores16<DENSE>(p, rc, &acc[0], key0 + c * 32, s);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) mx = fmaxf(mx, s[i]);
-        if (two) {
-          scores16<DENSE>(p, rc, &acc[16], key0 + c * 32 + 16, s);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, s[i]);
-        }
-      }
-      const float m_new = fmaxf(m, mx);
-      const float sub = m_new == -INFINITY ? 0.f : m_new;
-      const float corr = ex2_approx(m - sub);                      // m = -inf -> 0
-      m = m_new;
-      // ---- rescale the running output in TMEM when some row's maximum moved
-      if (it > 0) {
-        mbar_wait(o_full, (it - 1) & 1);                           // P V_{it-1} has landed in the O columns
-        tc_fence_after();
-        if (!__all_sync(0xffffffffu, corr == 1.0f)) {
-#pragma unroll 1
-          for (int c = 0; c < HD / 32; ++c) {
-            uint32_t acc[32];
-            tmem_ld16(t_row + C::O_COL + c * 32, *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));
-            tmem_ld16(t_row + C::O_COL + c * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&acc[16]));
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) * corr);
-            tmem_st16(t_row + C::O_COL + c * 32, *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));
-            tmem_st16(t_row + C::O_COL + c * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&acc[16]));
-          }
-          tmem_st_wait();
-        }
-      }
-      // ---- pass 2: p = exp2(s - m), row sum, P (bf16) into the K-major SW128 layout
-      float rs = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < nchunks; ++c) {
-        uint32_t acc[32];
-        const bool two = (c * 32 + 16) < n_eff;
-        tmem_ld16(t_row + c * 32, *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));
-        if (two) tmem_ld16(t_row + c * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&acc[16]));
-        tmem_ld_wait();
-        uint32_t w[16];
-        float s[16];
-        scores16<DENSE>(p, rc, &acc[0], key0 + c * 32, s);
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          const float p0 = ex2_approx(s[i] - sub), p1 = ex2_approx(s[i + 1] - sub);
-          rs += p0 + p1;
-          w[i >> 1] = pack_bf16x2(p0, p1);
-        }
-        if (two) {
-          scores16<DENSE>(p, rc, &acc[16], key0 + c * 32 + 16, s);
-#pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            const float p0 = ex2_approx(s[i] - sub), p1 = ex2_approx(s[i + 1] - sub);
-            rs += p0 + p1;
-            w[8 + (i >> 1)] = pack_bf16x2(p0, p1);
-          }
-        }
-        // 32 keys = 64 bytes = four 16-byte pieces; piece index inside the 64-key atom: (c & 1) * 4 + j
-        const uint32_t blk = p_row + (c >> 1) * C::Q_ATOM;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (j < 2 || two) {
-            const int piece = (c & 1) * 4 + j;
-            st_shared_v4(blk + ((piece ^ sw) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-          }
-        }
-      }
-      l = l * corr + rs;
-      fence_proxy_async_smem();                                    // generic-proxy writes of P -> visible to the MMA
-      tc_fence_before();
-      mbar_arrive(p_full);
-    }
-    // ---- normalise and store this row; log2-domain LSE
-    if (nsteps > 0) {
-      mbar_wait(o_full, (nsteps - 1) & 1);
-      tc_fence_after();
-    }
-    const float inv = l > 0.f ? 1.f / l : 0.f;
-    __nv_bfloat16* op = p.out + b * p.o_bs + (long long)row * p.ldo + h * HD;
-#pragma unroll 1
-    for (int c = 0; c < HD / 32; ++c) {
-      uint32_t acc[32];
-      if (nsteps > 0) {   // block-uniform: tcgen05.ld is .sync.aligned, it must never sit under a per-row condition
-        tmem_ld16(t_row + C::O_COL + c * 32, *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));
-        tmem_ld16(t_row + C::O_COL + c * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&acc[16]));
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] = 0u;
-      }
-      if (row < p.nq) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 v;
-          v.x = pack_bf16x2(__uint_as_float(acc[8 * j]) * inv, __uint_as_float(acc[8 * j + 1]) * inv);
-          v.y = pack_bf16x2(__uint_as_float(acc[8 * j + 2]) * inv, __uint_as_float(acc[8 * j + 3]) * inv);
-          v.z = pack_bf16x2(__uint_as_float(acc[8 * j + 4]) * inv, __uint_as_float(acc[8 * j + 5]) * inv);
-          v.w = pack_bf16x2(__uint_as_float(acc[8 * j + 6]) * inv, __uint_as_float(acc[8 * j + 7]) * inv);
-          if (!(l > 0.f)) v = make_uint4(0u, 0u, 0u, 0u);          // rows without any mass: exact zeros
-          *reinterpret_cast<uint4*>(op + c * 32 + 8 * j) = v;
-        }
-      }
-    }
-    if (row < p.nq && p.lse != nullptr) p.lse[((long long)b * p.heads + h) * p.nq + row] = l > 0.f ? m + log2f(l) : 0.f;
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 4) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
-  }
-}
-
-// ================================================================================================ forward, pipelined
-// Second-generation forward: 64-key tiles for both head dims, the S accumulator double-buffered in TMEM (S_{j+1} = Q K_{j+1}^T
+// ================================================================================================ forward
+// Forward kernel (second generation; the first one used 128-key tiles, two passes over S and a single S buffer and was
+// 25 % slower, profiles/r02_attention_by_shape.md): 64-key tiles for both head dims, the S accumulator double-buffered in TMEM (S_{j+1} = Q K_{j+1}^T
 // is issued while the softmax warps work on S_j), a two-stage K ring, the scores of a tile held in registers (one TMEM
 // read, one pass), and FA4-style lazy rescaling: the running output in TMEM is only rescaled when some row's maximum
 // grew by more than 2^8 since the value the accumulators are expressed in (p <= 256 is harmless in fp32 / bf16), so
@@ -1222,37 +925,29 @@ static void fill_params(const Args& a, Params& p) {
   p.mask_mode = a.dense ? 0 : a.mask_mode; p.kpm = a.kpm > 0 ? a.kpm : 64; p.causal = a.causal; p.dq_direct = 0;
 }
 
-static bool fwd_v1_forced() {
-  static int mode = -1;
-  if (mode < 0) { const char* e = getenv("OFK_ATTN_FWD_V1"); mode = (e && atoi(e) != 0) ? 1 : 0; }
-  return mode == 1;
-}
-
 template <int HD, bool DENSE>
 static int launch_fwd(const Args& a) {
-  const bool v1 = fwd_v1_forced();
-  const int bkt = v1 ? FwdCfg<HD>::BKT : Fwd2Cfg<HD>::BKT;
-  const int smem_bytes = v1 ? FwdCfg<HD>::SMEM : Fwd2Cfg<HD>::SMEM;
+  using C = Fwd2Cfg<HD>;
   CUtensorMap tq, tk, tv;
   int rc = ofk_tensor_map_bf16(a.q, a.ldq, a.batch * a.nq, a.heads * HD, 64, 128, &tq);
   if (rc) return rc;
-  rc = ofk_tensor_map_bf16(a.k, a.ldk, a.batch * a.nk, a.heads * HD, 64, bkt, &tk);
+  rc = ofk_tensor_map_bf16(a.k, a.ldk, a.batch * a.nk, a.heads * HD, 64, C::BKT, &tk);
   if (rc) return rc;
-  rc = ofk_tensor_map_bf16(a.v, a.ldv, a.batch * a.nk, a.heads * HD, 64, bkt, &tv);
+  rc = ofk_tensor_map_bf16(a.v, a.ldv, a.batch * a.nk, a.heads * HD, 64, C::BKT, &tv);
   if (rc) return rc;
-  auto kern = v1 ? attn_fwd_tc_kernel<HD, DENSE> : attn_fwd2_tc_kernel<HD, DENSE>;
-  static bool attr_done[2] = {false, false};
-  if (!attr_done[v1 ? 1 : 0]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  auto kern = attn_fwd2_tc_kernel<HD, DENSE>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) return ofk_set_error(OFK_ERR_CUDA, cudaGetErrorString(e));
-    attr_done[v1 ? 1 : 0] = true;
+    attr_done = true;
   }
   Params p;
   fill_params(a, p);
   int q_tiles = (a.nq + 127) / 128;
   if (a.q_tile_limit > 0 && a.q_tile_limit < q_tiles) q_tiles = a.q_tile_limit;
   dim3 grid(q_tiles, a.heads, a.batch);
-  kern<<<grid, FWD_THREADS, smem_bytes, (cudaStream_t)a.stream>>>(tq, tk, tv, p);
+  kern<<<grid, FWD_THREADS, C::SMEM, (cudaStream_t)a.stream>>>(tq, tk, tv, p);
   OFK_CHECK_LAUNCH();
   ++g_tc_launches;
   return 0;

@@ -30,7 +30,8 @@ f32 = torch.float32
 
 _w16_cache = {}
 
-# set by train.GradBucket: called with a gated block's parameter tuple once its backward kernels are enqueued
+# set by train.GradBucket: called with a block's parameter tuple (gated block, resampler layer, final norm) once its
+# backward kernels are enqueued
 block_backward_hook = None
 
 
@@ -317,6 +318,8 @@ class PerceiverLayerFn(torch.autograd.Function):
                                  dbeta=sinks["nl_b"].buffer(), dx=dlat, dx_add=dlat, rows_per_group=n,
                                  group_stride=v + n, group_offset=v)
         grads = [sinks[nm].result() for nm in names]
+        if block_backward_hook is not None:
+            block_backward_hook(ctx.params)
         return (dx_media.view(U, v, Dv) if (needs[0] and dx_media is not None) else None,
                 dlat.view(U, n, Dv) if needs[1] else None, None, *grads)
 
@@ -347,6 +350,8 @@ class FinalNormFn(torch.autograd.Function):
             dy2d = dy2d.float()
         dx = ops.layernorm_bwd(dy2d, x2d, w, mean, rstd, dgamma=sw.buffer(), dbeta=sb.buffer(),
                                want_dx=ctx.needs_input_grad[0])
+        if block_backward_hook is not None:
+            block_backward_hook(ctx.params)
         return (dx.view(dy.shape) if dx is not None else None), sw.result(), sb.result()
 
 
@@ -502,4 +507,6 @@ class PerceiverFoldedLayerFn(torch.autograd.Function):
         dlat = ops.layernorm_bwd(dlatn_kv, lat2d, nl_w, l_mean, l_rstd, dgamma=sinks["nl_w"].buffer(),
                                  dbeta=sinks["nl_b"].buffer(), dx=dlat, dx_add=dlat)
         grads = [sinks[nm].result() for nm in names]
+        if block_backward_hook is not None:
+            block_backward_hook(ctx.params)
         return (None, dlat.view(U, n, Dv) if needs[1] else None, None, None, *grads)

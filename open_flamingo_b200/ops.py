@@ -36,9 +36,12 @@ def _gemm_workspace(device):
 
 
 _comm_in_flight = False
-# SMs every persistent GEMM grid leaves to NCCL while gradient-chunk all-reduces are in flight (0 = none); the
-# environment variable lets bench.py / a launcher pick it per run without code changes
-COMM_RESERVED_SMS = int(os.environ.get("OFK_COMM_RESERVE_SMS", "0"))
+# SMs every persistent GEMM grid leaves to NCCL while gradient-chunk all-reduces are in flight (world > 1 only; 0 = none).
+# Measured at N = 2 inside the captured step (profiles/r02_ddp_timeline_n2.md): with all 148 SMs owned by the GEMM grids the
+# all-reduce kernels are starved (30.8 ms of NCCL kernel time) and the ~60 GEMMs that run beside them take 1.3-1.55 x longer
+# (static tile schedule: the clusters that cannot become resident do their share afterwards) -- 121.1 ms / step; with 16 SMs
+# left free (and NCCL_MAX_CTAS=16, see train.configure_nccl_for_overlap) 117.7 ms.
+COMM_RESERVED_SMS = int(os.environ.get("OFK_COMM_RESERVE_SMS", "16"))
 
 
 def set_comm_in_flight(flag):

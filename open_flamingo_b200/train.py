@@ -26,6 +26,16 @@ from . import fused, ops
 ALIGN = 64  # elements; keeps every parameter view 256-byte (fp32) / 128-byte (bf16) aligned for TMA
 
 
+def configure_nccl_for_overlap():
+    """Call BEFORE torch.distributed.init_process_group(backend="nccl").  Caps the CTAs NCCL uses per collective at the
+    number of SMs the persistent GEMM grids leave free while gradient chunks are being reduced (ops.COMM_RESERVED_SMS), so
+    the all-reduce kernels run BESIDE the backward GEMMs instead of fighting them for SMs.  Respects an NCCL_MAX_CTAS the
+    launcher already set."""
+    import os
+    if ops.COMM_RESERVED_SMS > 0:
+        os.environ.setdefault("NCCL_MAX_CTAS", str(ops.COMM_RESERVED_SMS))
+
+
 def hot_path_parameters(model):
     """[(name, param)] of the trainable hot-path parameters in backward-completion order."""
     lm = model.lang_encoder
@@ -38,9 +48,32 @@ def hot_path_parameters(model):
         ps = [(f"lang_encoder.gated_cross_attn_layers.{i}.{n}", p) for n, p in blk.named_parameters() if p.requires_grad]
         if ps:
             groups.append(("xattn", i, ps))
-    ps = [(f"perceiver.{n}", p) for n, p in model.perceiver.named_parameters() if p.requires_grad]
-    if ps:
-        groups.append(("perceiver", -1, ps))
+    per = model.perceiver
+    named = [(n, p) for n, p in per.named_parameters() if p.requires_grad]
+    if hasattr(per, "layers") and hasattr(per, "norm") and all(hasattr(l, "__getitem__") for l in per.layers):
+        # The resampler's backward runs last (its output feeds every gated block) and takes ~2 ms: one group per piece
+        # in the order their gradients become final -- final norm, layers depth-1 .. 0, then whatever autograd itself
+        # accumulates at the very end (latents, optional frame / media-time embeddings) -- so that only the last,
+        # small piece of the all-reduce is exposed after the backward instead of the whole 63 M-parameter resampler.
+        taken = set()
+
+        def take(prefix):
+            ps = [(f"perceiver.{n}", p) for n, p in named if n.startswith(prefix)]
+            taken.update(n for n, _ in named if n.startswith(prefix))
+            return ps
+
+        ps = take("norm.")
+        if ps:
+            groups.append(("perceiver_norm", -1, ps))
+        for j in reversed(range(len(per.layers))):
+            ps = take(f"layers.{j}.")
+            if ps:
+                groups.append(("perceiver_layer", j, ps))
+        ps = [(f"perceiver.{n}", p) for n, p in named if n not in taken]
+        if ps:
+            groups.append(("perceiver", -1, ps))
+    elif named:
+        groups.append(("perceiver", -1, [(f"perceiver.{n}", p) for n, p in named]))
     return groups
 
 
@@ -104,18 +137,24 @@ class GradBucket:
             if last_of_chunk:
                 self.chunks.append((start, group_end[g]))
                 start = group_end[g]
-        if start < self.total:
-            for g in range(len(groups)):
-                if groups[g][0] != "xattn":
-                    self.group_to_chunk[g] = len(self.chunks)
-            self.chunks.append((start, self.total))
-        # the gate parameter identifies a gated block from inside its backward
-        self._gate_to_group = {}
+        # the remaining groups (resampler pieces, in backward-completion order) form two chunks: everything but the last
+        # two pieces (final norm, layers depth-1 .. 1) is reduced while layer 0's backward still runs; only layer 0 + the
+        # autograd-accumulated leftovers (latents, embeddings) -- a sixth of the resampler -- are reduced after the backward
+        rest = [g for g in range(len(groups)) if groups[g][0] != "xattn"]
+        parts = [rest[:-2], rest[-2:]] if len(rest) >= 3 else [[g] for g in rest]
+        for part in parts:
+            if not part:
+                continue
+            for g in part:
+                self.group_to_chunk[g] = len(self.chunks)
+            self.chunks.append((start, group_end[part[-1]]))
+            start = group_end[part[-1]]
+        assert start == self.total
+        # any parameter of a block identifies its group from inside the block's backward
+        self._param_to_group = {}
         for g, (kind, idx, ps) in enumerate(groups):
-            if kind == "xattn":
-                for name, p in ps:
-                    if name.endswith("attn_gate"):
-                        self._gate_to_group[id(p)] = g
+            for name, p in ps:
+                self._param_to_group[id(p)] = g
         self._chunk_last_group = {}
         for g, c in self.group_to_chunk.items():
             self._chunk_last_group[c] = max(self._chunk_last_group.get(c, -1), g)
@@ -168,8 +207,14 @@ class GradBucket:
         return _NoSync()
 
     def on_block_backward_done(self, params):
-        """Called by fused.GatedXattnBlockFn.backward once a block's gradient kernels are enqueued."""
-        g = self._gate_to_group.get(id(params[5]))  # params[5] is attn_gate
+        """Called by the fused backward of a gated block / resampler layer / final norm once its gradient kernels are
+        enqueued (fused.block_backward_hook), with that block's parameter tuple."""
+        g = None
+        for p in params:
+            if p is not None:
+                g = self._param_to_group.get(id(p))
+                if g is not None:
+                    break
         if g is None:
             return
         c = self.group_to_chunk[g]

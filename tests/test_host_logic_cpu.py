@@ -142,3 +142,34 @@ def test_conditioning_plumbing_on_cpu():
     lm.clear_conditioned_layers()
     assert not lm.is_conditioned()
     assert all(layer.vis_x is None and layer.media_locations is None for layer in lm._get_decoder_layers())
+
+
+def test_gradient_bucket_layout_splits_the_resampler_in_backward_order():
+    """train.hot_path_parameters / GradBucket: gated blocks last-to-first, then the resampler in the order its gradients
+    become final (final norm, layers depth-1..0, then latents), the resampler cut into two chunks, every trainable
+    hot-path parameter exactly once, chunks contiguous and ending on group boundaries."""
+    from open_flamingo_b200.testing import build_flamingo
+    from open_flamingo_b200.train import GradBucket, hot_path_parameters
+    vit = dict(image_size=56, patch_size=14, width=128, layers=1, heads=2, output_dim=128)
+    mpt = dict(d_model=128, n_heads=2, n_layers=4, vocab_size=61, max_seq_len=64, expansion_ratio=2)
+    model, _, _ = build_flamingo(vit, mpt, cross_attn_every_n_layers=2, device="cpu", seed=0)
+    groups = hot_path_parameters(model)
+    kinds = [(k, i) for k, i, _ in groups]
+    depth = len(model.perceiver.layers)
+    assert kinds == [("xattn", 3), ("xattn", 1), ("perceiver_norm", -1)] + [("perceiver_layer", j) for j in reversed(range(depth))] + \
+        [("perceiver", -1)]
+    assert [n for n, _ in groups[-1][2]] == ["perceiver.latents"]
+    names = [n for _, _, ps in groups for n, _ in ps]
+    want = {n for n, p in model.named_parameters(remove_duplicate=False)
+            if p.requires_grad and n.startswith(("perceiver.", "lang_encoder.gated_cross_attn_layers."))}
+    assert len(names) == len(set(names)) and set(names) == want
+    bucket = GradBucket(groups, num_chunks=3, flatten_params=False)
+    assert bucket.chunks[0][0] == 0 and bucket.chunks[-1][1] == bucket.total
+    assert all(a[1] == b[0] for a, b in zip(bucket.chunks, bucket.chunks[1:]))
+    # 2 xattn chunks (num_chunks - 1) + the resampler in two: [norm, layers depth-1 .. 1] closes when layer 1's backward is
+    # done and overlaps layer 0's; [layer 0, latents] is what remains for after the backward
+    assert len(bucket.chunks) == 2 + 2
+    n_groups = len(groups)
+    assert bucket.group_to_chunk[n_groups - 1] == bucket.group_to_chunk[n_groups - 2] == len(bucket.chunks) - 1
+    assert all(bucket.group_to_chunk[g] == len(bucket.chunks) - 2 for g in range(2, n_groups - 2))
+    assert bucket._chunk_last_group[len(bucket.chunks) - 2] == n_groups - 3

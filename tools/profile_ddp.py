@@ -24,6 +24,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        from open_flamingo_b200.train import configure_nccl_for_overlap
+        configure_nccl_for_overlap()
         dist.init_process_group("nccl", device_id=dev)
     vit_cfg, mpt_kw, every = bench.model_dims("of3b")
     import contextlib
