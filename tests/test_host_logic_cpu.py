@@ -173,3 +173,31 @@ def test_gradient_bucket_layout_splits_the_resampler_in_backward_order():
     assert bucket.group_to_chunk[n_groups - 1] == bucket.group_to_chunk[n_groups - 2] == len(bucket.chunks) - 1
     assert all(bucket.group_to_chunk[g] == len(bucket.chunks) - 2 for g in range(2, n_groups - 2))
     assert bucket._chunk_last_group[len(bucket.chunks) - 2] == n_groups - 3
+
+
+def test_sm_reservation_contract_and_nccl_cta_cap(monkeypatch):
+    """Host-side state only (no launch): ofk_gemm_reserve_sms clamps to whole SM pairs in [0, 64] and returns the previous
+    value; ops.set_comm_in_flight toggles it around the all-reduce window; configure_nccl_for_overlap caps NCCL's CTAs at
+    the same number unless the launcher already chose one."""
+    import __graft_entry__ as g
+    g.build()
+    from open_flamingo_b200 import _lib, ops, train
+    lib = _lib.lib()
+    lib.ofk_gemm_reserve_sms(0)
+    assert lib.ofk_gemm_reserve_sms(17) == 0
+    assert lib.ofk_gemm_reserve_sms(1000) == 16      # 17 -> 16: whole pairs
+    assert lib.ofk_gemm_reserve_sms(-5) == 64        # clamped
+    assert lib.ofk_gemm_reserve_sms(0) == 0
+    assert ops.COMM_RESERVED_SMS > 0, "default build reserves SMs while gradient chunks are in flight"
+    ops.set_comm_in_flight(True)
+    assert lib.ofk_gemm_reserve_sms(ops.COMM_RESERVED_SMS) == (ops.COMM_RESERVED_SMS & ~1)
+    ops.set_comm_in_flight(False)
+    assert lib.ofk_gemm_reserve_sms(0) == 0
+    monkeypatch.setenv("NCCL_MAX_CTAS", "0")   # so that teardown restores whatever the environment had
+    monkeypatch.delenv("NCCL_MAX_CTAS")
+    train.configure_nccl_for_overlap()
+    import os
+    assert os.environ["NCCL_MAX_CTAS"] == str(ops.COMM_RESERVED_SMS)
+    monkeypatch.setenv("NCCL_MAX_CTAS", "4")
+    train.configure_nccl_for_overlap()
+    assert os.environ["NCCL_MAX_CTAS"] == "4"
